@@ -1,0 +1,28 @@
+"""drawingspinup_b200 - B200-native engine for DrawingSpinUp's per-frame stylization hot path.
+
+Public surface (mirrors ``3_style_translator/training/models.py`` for the inference path):
+
+* :class:`GeneratorJ_RIC`, :class:`GeneratorJ` - drop-in classes for ``training.models``.
+* :func:`install` - rebind those two names inside the reference's ``training.models`` so that
+  ``training.trainers.build_model`` (trainers.py:33-35) builds the B200 engine.
+* :mod:`drawingspinup_b200.pipeline` - device-resident stage-1 -> stage-2 frame pipeline with
+  frame sharding across GPUs; :mod:`drawingspinup_b200.run` - launcher for the unmodified
+  ``test_stage1.py`` / ``test_stage2.py``.
+"""
+from .models import GeneratorJ, GeneratorJ_RIC, ric_offsets  # noqa: F401
+
+__all__ = ["GeneratorJ", "GeneratorJ_RIC", "ric_offsets", "install"]
+
+
+def install(models_module=None):
+    """Rebind ``GeneratorJ_RIC`` / ``GeneratorJ`` in the reference's ``training.models`` module.
+
+    ``build_model`` resolves the class by name at call time (``getattr(m, model_type)``,
+    trainers.py:33-35), so after this call the unmodified reference scripts construct, load and
+    call the B200 engine.  Returns the patched module."""
+    if models_module is None:
+        import importlib
+        models_module = importlib.import_module("training.models")
+    models_module.GeneratorJ_RIC = GeneratorJ_RIC
+    models_module.GeneratorJ = GeneratorJ
+    return models_module

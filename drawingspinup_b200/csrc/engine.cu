@@ -1,0 +1,759 @@
+// Network planner + C ABI (include/dsu_b200.h) of the stylization engine.
+//
+// Turns the constructor arguments of GeneratorJ / GeneratorJ_RIC (training/models.py:24-111,
+// 200-291) and a loaded state dict into a list of fused convolution launches (conv_umma.cu):
+// BatchNorm (eval) is folded into per-channel scale/shift, conv weights are rounded to fp16
+// (hi [+lo]) and pre-swizzled into tensor-core tiles, skip connections / nearest-x2 upsampling /
+// stride / concat become slot tables, and the dead stage-1 smoother conv (models.py:348-350) is
+// dropped.  Activations live in NHWC fp16 workspace buffers owned by the handle.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../../include/dsu_b200.h"
+#include "conv.cuh"
+#include "frames.cuh"
+
+using namespace dsu;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return fail(DSU_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));      \
+    } while (0)
+
+enum BufId { SK0 = 0, P0, O1, P1, O2, TT, UU, V2, V1, C11, S0, NBUF };
+
+struct SegDef {
+    int buf, choff, nch;   // buffer, first channel, channels consumed (multiple of 8)
+    int wch0, wn;          // first weight input channel, real weight channels (<= nch)
+};
+
+struct LayerDef {
+    std::string name, wkey, bkey, bn, bn2;
+    int k = 3, pad = 1, stride = 1, up = 0, ric = 0, cout = 0, level_out = 0;
+    std::vector<SegDef> segs;
+    int act = 0;
+    int out_buf = -1, out_choff = 0, out_relu = 0, out2_buf = -1;
+    int resid_in = 0, resid_out = 0, final = 0;
+    // compiled at finalize
+    int nchunks = 0;
+    Slot* d_slots = nullptr;
+    ChunkHdr* d_hdrs = nullptr;
+    uint8_t* d_wpack = nullptr;
+    float *d_scale = nullptr, *d_shift = nullptr, *d_scale2 = nullptr, *d_shift2 = nullptr;
+    double macs_per_px = 0;   // live MACs per output pixel
+};
+
+struct Step {
+    int type;    // 0 conv, 1 maxpool
+    int layer;
+    int src, src_choff, C, dst;
+};
+
+struct Level {
+    int h = 0, w = 0;
+    float4* w4 = nullptr;
+    char4* off = nullptr;
+};
+
+}  // namespace
+
+struct dsu_engine {
+    dsu_config cfg{};
+    int cin_pad = 8;
+    bool exact = false, finalized = false;
+    std::map<std::string, std::vector<int64_t>> expected;
+    std::vector<std::string> expected_order;
+    std::map<std::string, std::vector<float>> w;
+    std::set<std::string> loaded;
+    std::vector<LayerDef> layers;
+    std::vector<Step> steps;
+    int buf_level[NBUF]{}, buf_C[NBUF]{};
+    bool buf_used[NBUF]{};
+    float *d_w12 = nullptr, *d_b12 = nullptr;
+    // shape-dependent state
+    int B = 0, H = 0, W = 0;
+    __half* buf_hi[NBUF]{};
+    __half* buf_lo[NBUF]{};
+    size_t buf_cap[NBUF]{};
+    float* resid = nullptr;
+    size_t resid_cap = 0;
+    Level lv[3];
+    std::map<std::pair<int, int>, std::vector<float>> user_offsets;
+    uint8_t *io_color = nullptr, *io_pos = nullptr, *io_edge = nullptr, *io_out = nullptr;
+    size_t io_cap = 0;
+};
+
+namespace {
+
+// ------------------------------------------------------------------ configuration -> plan
+std::string conv12_prefix(const dsu_config& c) { return c.tanh ? "conv_12.0" : "conv_12"; }
+
+void expect(dsu_engine* E, const std::string& key, std::vector<int64_t> shape) {
+    E->expected[key] = shape;
+    E->expected_order.push_back(key);
+}
+
+void expect_bn(dsu_engine* E, const std::string& p, int c) {
+    expect(E, p + ".weight", {c});
+    expect(E, p + ".bias", {c});
+    expect(E, p + ".running_mean", {c});
+    expect(E, p + ".running_var", {c});
+    expect(E, p + ".num_batches_tracked", {});
+}
+
+int build_plan(dsu_engine* E) {
+    const dsu_config& c = E->cfg;
+    const int* f = c.filters;
+    const bool ric = c.kind == DSU_KIND_GENERATORJ_RIC;
+    const bool bn = c.norm == DSU_NORM_BATCH;
+    const int cin = c.input_channels, cp = E->cin_pad;
+    const int k0 = ric ? 3 : 7;
+    auto conv_keys = [&](const std::string& p, int co, int ci, int k, bool may_bias) {
+        expect(E, p + ".weight", {co, ci, k, k});
+        if (may_bias && c.use_bias) expect(E, p + ".bias", {co});
+    };
+    // state-dict layout (models.py:41-111 / 220-284)
+    conv_keys("conv0.conv", f[0], cin, k0, true);
+    if (bn) expect_bn(E, "conv0.normalization", f[0]);
+    conv_keys("conv1.conv", f[1], f[0], 3, true);
+    if (bn) expect_bn(E, "conv1.normalization", f[1]);
+    conv_keys("conv2.conv", f[2], f[1], 3, true);
+    if (bn) expect_bn(E, "conv2.normalization", f[2]);
+    for (int i = 0; i < c.resnet_blocks; ++i) {
+        const std::string p = "resnets." + std::to_string(i) + ".";
+        conv_keys(p + "conv_0", f[2], f[2], 3, true);
+        if (bn) expect_bn(E, p + "normalization", f[2]);
+        conv_keys(p + "conv_1", f[2], f[2], 3, true);
+    }
+    conv_keys("upconv2.1", f[4], f[3] + f[2], 3, false);
+    if (bn) expect_bn(E, "upconv2.2", f[4]);
+    conv_keys("upconv1.1", f[4], f[4] + f[1], 3, false);
+    if (bn) expect_bn(E, "upconv1.2", f[4]);
+    conv_keys("conv_11.0", f[5], f[0] + f[4] + cin, k0, true);
+    if (c.append_smoothers) {
+        conv_keys("conv_11_a.0", f[5], f[5], 3, true);
+        expect_bn(E, "conv_11_a.2", f[5]);
+        conv_keys("conv_11_a.3", f[5], f[5], 3, true);
+    }
+    expect(E, conv12_prefix(c) + ".weight", {3, f[5], 1, 1});
+    expect(E, conv12_prefix(c) + ".bias", {3});
+
+    // activation buffers
+    auto setbuf = [&](int b, int level, int C) { E->buf_level[b] = level; E->buf_C[b] = C; E->buf_used[b] = true; };
+    setbuf(SK0, 0, f[0] + cp);
+    setbuf(O1, 1, f[1]);
+    setbuf(O2, 2, f[2]);
+    if (ric) { setbuf(P0, 1, f[0]); setbuf(P1, 2, f[1]); }
+    if (c.resnet_blocks > 0) { setbuf(TT, 2, f[2]); setbuf(UU, 2, f[2]); }
+    setbuf(V2, 1, f[4]);
+    setbuf(V1, 0, f[4]);
+    setbuf(C11, 0, f[5]);
+    if (c.append_smoothers && !ric) setbuf(S0, 0, f[5]);
+
+    // in stage 1 the deformable calls pass only .weight, so conv biases are never applied (models.py:302-351)
+    auto bias_of = [&](const std::string& p) { return (c.use_bias && !ric) ? p + ".bias" : std::string(); };
+    auto add = [&](LayerDef L) { E->layers.push_back(L); E->steps.push_back(Step{0, (int)E->layers.size() - 1, 0, 0, 0, 0}); };
+    {
+        LayerDef L; L.name = "conv0"; L.wkey = "conv0.conv.weight"; L.bkey = bias_of("conv0.conv");
+        L.bn = bn ? "conv0.normalization" : ""; L.k = k0; L.pad = k0 / 2; L.ric = ric; L.cout = f[0]; L.level_out = 0;
+        L.segs = {{SK0, f[0], cp, 0, cin}}; L.act = 2; L.out_buf = SK0; L.out_choff = 0;
+        add(L);
+    }
+    if (ric) E->steps.push_back(Step{1, -1, SK0, 0, f[0], P0});
+    {
+        LayerDef L; L.name = "conv1"; L.wkey = "conv1.conv.weight"; L.bkey = bias_of("conv1.conv");
+        L.bn = bn ? "conv1.normalization" : ""; L.stride = ric ? 1 : 2; L.ric = ric; L.cout = f[1]; L.level_out = 1;
+        L.segs = {{ric ? P0 : SK0, 0, f[0], 0, f[0]}}; L.act = 2; L.out_buf = O1;
+        add(L);
+    }
+    if (ric) E->steps.push_back(Step{1, -1, O1, 0, f[1], P1});
+    const bool has_res = c.resnet_blocks > 0;
+    {
+        LayerDef L; L.name = "conv2"; L.wkey = "conv2.conv.weight"; L.bkey = bias_of("conv2.conv");
+        L.bn = bn ? "conv2.normalization" : ""; L.stride = ric ? 1 : 2; L.ric = ric; L.cout = f[2]; L.level_out = 2;
+        L.segs = {{ric ? P1 : O1, 0, f[1], 0, f[1]}}; L.act = 2;
+        if (has_res) { L.out_buf = TT; L.out_relu = 1; L.out2_buf = O2; L.resid_out = 1; }
+        else L.out_buf = O2;
+        add(L);
+    }
+    for (int i = 0; i < c.resnet_blocks; ++i) {
+        const std::string p = "resnets." + std::to_string(i) + ".";
+        LayerDef A; A.name = p + "conv_0"; A.wkey = p + "conv_0.weight"; A.bkey = bias_of(p + "conv_0");
+        A.bn = bn ? p + "normalization" : ""; A.ric = ric; A.cout = f[2]; A.level_out = 2;
+        A.segs = {{TT, 0, f[2], 0, f[2]}}; A.act = 1; A.out_buf = UU;
+        add(A);
+        LayerDef Bl; Bl.name = p + "conv_1"; Bl.wkey = p + "conv_1.weight"; Bl.bkey = bias_of(p + "conv_1");
+        Bl.ric = ric; Bl.cout = f[2]; Bl.level_out = 2;
+        Bl.segs = {{UU, 0, f[2], 0, f[2]}}; Bl.act = 0; Bl.resid_in = 1; Bl.resid_out = 1;
+        Bl.out_buf = TT; Bl.out_relu = (i + 1 < c.resnet_blocks) ? 1 : 0;
+        add(Bl);
+    }
+    {
+        LayerDef L; L.name = "upconv2"; L.wkey = "upconv2.1.weight"; L.bn = bn ? "upconv2.2" : "";
+        L.up = 1; L.ric = ric; L.cout = f[4]; L.level_out = 1;
+        L.segs = {{has_res ? TT : O2, 0, f[2], 0, f[2]}, {O2, 0, f[2], f[3], f[2]}}; L.act = 1; L.out_buf = V2;
+        add(L);
+    }
+    {
+        LayerDef L; L.name = "upconv1"; L.wkey = "upconv1.1.weight"; L.bn = bn ? "upconv1.2" : "";
+        L.up = 1; L.ric = ric; L.cout = f[4]; L.level_out = 0;
+        L.segs = {{V2, 0, f[4], 0, f[4]}, {O1, 0, f[1], f[4], f[1]}}; L.act = 1; L.out_buf = V1;
+        add(L);
+    }
+    {
+        LayerDef L; L.name = "conv_11"; L.wkey = "conv_11.0.weight"; L.bkey = bias_of("conv_11.0");
+        L.k = k0; L.pad = k0 / 2; L.ric = ric; L.cout = f[5]; L.level_out = 0;
+        L.segs = {{V1, 0, f[4], 0, f[4]}, {SK0, 0, f[0], f[4], f[0]}, {SK0, f[0], cp, f[4] + f[0], cin}};
+        L.act = 1;
+        if (c.append_smoothers) L.out_buf = C11; else L.final = 1;
+        add(L);
+    }
+    if (c.append_smoothers) {
+        if (!ric) {   // stage 1: this conv is dead code (models.py:348-350) and is skipped
+            LayerDef L; L.name = "conv_11_a.0"; L.wkey = "conv_11_a.0.weight"; L.bkey = bias_of("conv_11_a.0");
+            L.bn2 = "conv_11_a.2"; L.cout = f[5]; L.level_out = 0;
+            L.segs = {{C11, 0, f[5], 0, f[5]}}; L.act = 1; L.out_buf = S0;
+            add(L);
+        }
+        LayerDef L; L.name = "conv_11_a.3"; L.wkey = "conv_11_a.3.weight"; L.bkey = bias_of("conv_11_a.3");
+        L.ric = ric; L.cout = f[5]; L.level_out = 0;
+        L.segs = {{ric ? C11 : S0, 0, f[5], 0, f[5]}}; L.act = 1; L.final = 1;
+        add(L);
+    }
+    return DSU_OK;
+}
+
+// ------------------------------------------------------------------ finalize: fold + pack
+template <typename T>
+int upload(T** dst, const std::vector<T>& src) {
+    if (*dst) { cudaFree(*dst); *dst = nullptr; }
+    if (src.empty()) return DSU_OK;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(dst), src.size() * sizeof(T)));
+    CUDA_TRY(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return DSU_OK;
+}
+
+int compile_layer(dsu_engine* E, LayerDef& L) {
+    const bool exact = E->exact;
+    const int C = L.cout, k = L.k;
+    const std::vector<float>& Wt = E->w.at(L.wkey);
+    int cin_total = 0;
+    for (const SegDef& s : L.segs) cin_total = std::max(cin_total, s.wch0 + s.wn);
+    if (Wt.size() != static_cast<size_t>(C) * cin_total * k * k) return fail(DSU_E_INVALID, "weight size mismatch for " + L.wkey);
+
+    struct HSlot { int kh, kw, seg, choff, wch, nvalid; };
+    std::vector<HSlot> hs;
+    double real_k = 0;
+    for (int kh = 0; kh < k; ++kh)
+        for (int kw = 0; kw < k; ++kw)
+            for (size_t si = 0; si < L.segs.size(); ++si) {
+                const SegDef& s = L.segs[si];
+                for (int c8 = 0; c8 < s.nch; c8 += 8)
+                    hs.push_back(HSlot{kh, kw, (int)si, s.choff + c8, s.wch0 + c8, std::max(0, std::min(8, s.wn - c8))});
+                real_k += s.wn;
+            }
+    L.macs_per_px = real_k * C;
+    const int nlog = static_cast<int>((hs.size() + 7) / 8);
+    const int per = exact ? 2 : 1;
+    L.nchunks = nlog * per;
+    std::vector<Slot> slots(static_cast<size_t>(L.nchunks) * 8);
+    std::vector<ChunkHdr> hdrs(L.nchunks);
+    const size_t tile = static_cast<size_t>(C) * 128;
+    std::vector<uint8_t> pack(static_cast<size_t>(nlog) * tile * (exact ? 3 : 1), 0);
+    size_t off = 0;
+    for (int q = 0; q < nlog; ++q) {
+        const int nslot = std::min<int>(8, (int)hs.size() - q * 8);
+        const int ksteps = (nslot + 1) / 2;
+        for (int pl = 0; pl < per; ++pl) {
+            const int qq = q * per + pl;
+            for (int j = 0; j < 8; ++j) {
+                Slot& sl = slots[static_cast<size_t>(qq) * 8 + j];
+                sl = Slot{0, 0, 0, 0, 0, 0};
+                if (j < nslot) {
+                    const HSlot& h = hs[q * 8 + j];
+                    sl.dy = static_cast<int8_t>(L.ric ? h.kh * 3 + h.kw : h.kh - L.pad);
+                    sl.dx = static_cast<int8_t>(L.ric ? 0 : h.kw - L.pad);
+                    sl.seg = static_cast<uint8_t>(h.seg + pl * (kMaxSeg / 2));
+                    sl.valid = 1;
+                    sl.choff = static_cast<uint16_t>(h.choff);
+                }
+            }
+            hdrs[qq].ksteps = static_cast<uint8_t>(ksteps);
+            hdrs[qq].wide = (exact && pl == 0) ? 1 : 0;
+            hdrs[qq].pad_ = 0;
+            hdrs[qq].b_off = static_cast<uint32_t>(off);
+            // B tile(s): row o = output channel, 128 B = 64 K elements, 16-byte groups XOR-swizzled by (row & 7)
+            const int nrows_sets = hdrs[qq].wide ? 2 : 1;
+            for (int set = 0; set < nrows_sets; ++set)
+                for (int o = 0; o < C; ++o)
+                    for (int j = 0; j < nslot; ++j) {
+                        const HSlot& h = hs[q * 8 + j];
+                        for (int ci = 0; ci < h.nvalid; ++ci) {
+                            const float wv = Wt[((static_cast<size_t>(o) * cin_total + h.wch + ci) * k + h.kh) * k + h.kw];
+                            const __half wh = __float2half_rn(wv);
+                            const __half val = (set == 0) ? wh : __float2half_rn(wv - __half2float(wh));
+                            const size_t row = static_cast<size_t>(set) * C + o;
+                            const size_t b = off + row * 128 + ((static_cast<size_t>(j) ^ (row & 7)) << 4) + ci * 2;
+                            std::memcpy(&pack[b], &val, 2);
+                        }
+                    }
+            off += tile * nrows_sets;
+        }
+    }
+    pack.resize(off);
+    int rc;
+    if ((rc = upload(&L.d_slots, slots))) return rc;
+    if ((rc = upload(&L.d_hdrs, hdrs))) return rc;
+    if ((rc = upload(&L.d_wpack, pack))) return rc;
+
+    // epilogue affine: y = act(acc * scale + shift) [* scale2 + shift2]
+    std::vector<float> scale(C, 1.0f), shift(C, 0.0f), scale2, shift2;
+    const std::vector<float>* bias = L.bkey.empty() ? nullptr : &E->w.at(L.bkey);
+    auto fold = [&](const std::string& p, std::vector<float>& sc, std::vector<float>& sh) {
+        const auto& g = E->w.at(p + ".weight"); const auto& b = E->w.at(p + ".bias");
+        const auto& m = E->w.at(p + ".running_mean"); const auto& v = E->w.at(p + ".running_var");
+        sc.resize(C); sh.resize(C);
+        for (int i = 0; i < C; ++i) {
+            const double inv = 1.0 / std::sqrt(static_cast<double>(v[i]) + 1e-5);
+            sc[i] = static_cast<float>(g[i] * inv);
+            sh[i] = static_cast<float>(b[i] - m[i] * g[i] * inv);
+        }
+    };
+    if (!L.bn.empty()) fold(L.bn, scale, shift);
+    if (bias) for (int i = 0; i < C; ++i) shift[i] += scale[i] * (*bias)[i];
+    if (!L.bn2.empty()) fold(L.bn2, scale2, shift2);
+    if ((rc = upload(&L.d_scale, scale))) return rc;
+    if ((rc = upload(&L.d_shift, shift))) return rc;
+    if ((rc = upload(&L.d_scale2, scale2))) return rc;
+    if ((rc = upload(&L.d_shift2, shift2))) return rc;
+    return DSU_OK;
+}
+
+// ------------------------------------------------------------------ RIC stencil tables
+// generate_coordinates (models.py:551-604) restated in float; used when the host binding did not
+// supply torch's own offsets through dsu_set_ric_offsets.
+std::vector<float> default_offsets(int h, int w) {
+    std::vector<float> off(static_cast<size_t>(18) * h * w, 0.0f);
+    const float ch = static_cast<float>(h) / 2.0f - 0.5f, cw = static_cast<float>(w) / 2.0f - 0.5f;
+    const float two_pi = static_cast<float>(M_PI) * 2.0f, step = two_pi / 8.0f;
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            float th = std::fmod(std::atan2(static_cast<float>(x) - cw, static_cast<float>(y) - ch), two_pi);
+            if (th < 0) th += two_pi;
+            th = std::nearbyint(10000.0f * th) / 10000.0f;
+            for (int rot = 0; rot < 8; ++rot) {
+                const int tap = rot < 4 ? rot : rot + 1;
+                const float ang = th + step * static_cast<float>(rot);
+                off[(static_cast<size_t>(2 * tap) * h + y) * w + x] = std::cos(ang) + static_cast<float>(1 - tap / 3);
+                off[(static_cast<size_t>(2 * tap + 1) * h + y) * w + x] = std::sin(ang) + static_cast<float>(1 - tap % 3);
+            }
+        }
+    return off;
+}
+
+// torchvision deform_conv2d bilinear rule -> per (tap, pixel) 4 weights and
+// clamped corner offsets.  Table order: 8 non-centre taps in raster order.
+int build_level(dsu_engine* E, Level& lv, int h, int w) {
+    if (lv.h == h && lv.w == w && lv.w4) return DSU_OK;
+    std::vector<float> off;
+    auto it = E->user_offsets.find({h, w});
+    off = (it != E->user_offsets.end()) ? it->second : default_offsets(h, w);
+    const size_t hw = static_cast<size_t>(h) * w;
+    std::vector<float4> w4(8 * hw);
+    std::vector<char4> o4(8 * hw);
+    for (int tap = 0; tap < 9; ++tap) {
+        if (tap == 4) continue;
+        const int t8 = tap < 4 ? tap : tap - 1;
+        const int i = tap / 3, j = tap % 3;
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x) {
+                const float py = static_cast<float>(y - 1 + i) + off[(static_cast<size_t>(2 * tap) * h + y) * w + x];
+                const float px = static_cast<float>(x - 1 + j) + off[(static_cast<size_t>(2 * tap + 1) * h + y) * w + x];
+                const bool inside = !(py <= -1.0f || py >= static_cast<float>(h) || px <= -1.0f || px >= static_cast<float>(w));
+                const float fl_y = std::floor(py), fl_x = std::floor(px);
+                const int hl = static_cast<int>(fl_y), wl = static_cast<int>(fl_x), hh_i = hl + 1, wh_i = wl + 1;
+                const float lh = py - fl_y, lw = px - fl_x, hh = 1.0f - lh, hw_ = 1.0f - lw;
+                const bool ok_hl = hl >= 0 && hl <= h - 1, ok_hh = hh_i >= 0 && hh_i <= h - 1;
+                const bool ok_wl = wl >= 0 && wl <= w - 1, ok_wh = wh_i >= 0 && wh_i <= w - 1;
+                float4 wv;
+                wv.x = (inside && ok_hl && ok_wl) ? hh * hw_ : 0.0f;
+                wv.y = (inside && ok_hl && ok_wh) ? hh * lw : 0.0f;
+                wv.z = (inside && ok_hh && ok_wl) ? lh * hw_ : 0.0f;
+                wv.w = (inside && ok_hh && ok_wh) ? lh * lw : 0.0f;
+                auto cl = [](int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); };
+                char4 ov;
+                ov.x = static_cast<signed char>(cl(hl, h - 1) - y);
+                ov.y = static_cast<signed char>(cl(hh_i, h - 1) - y);
+                ov.z = static_cast<signed char>(cl(wl, w - 1) - x);
+                ov.w = static_cast<signed char>(cl(wh_i, w - 1) - x);
+                w4[t8 * hw + static_cast<size_t>(y) * w + x] = wv;
+                o4[t8 * hw + static_cast<size_t>(y) * w + x] = ov;
+            }
+    }
+    int rc;
+    if ((rc = upload(&lv.w4, w4))) return rc;
+    if ((rc = upload(&lv.off, o4))) return rc;
+    lv.h = h; lv.w = w;
+    return DSU_OK;
+}
+
+// ------------------------------------------------------------------ workspace
+int ensure_shape(dsu_engine* E, int B, int H, int W) {
+    if (B <= 0 || H <= 0 || W <= 0 || (H % 4) || (W % 4))
+        return fail(DSU_E_INVALID, "frames must be [B>0, H, W] with H and W multiples of 4 (int(H/2), int(H/4) levels, models.py:296-300)");
+    for (int b = 0; b < NBUF; ++b) {
+        if (!E->buf_used[b]) continue;
+        const int l = E->buf_level[b];
+        const size_t bytes = static_cast<size_t>(B) * (H >> l) * (W >> l) * E->buf_C[b] * sizeof(__half);
+        if (bytes > E->buf_cap[b]) {
+            if (E->buf_hi[b]) cudaFree(E->buf_hi[b]);
+            if (E->buf_lo[b]) cudaFree(E->buf_lo[b]);
+            E->buf_hi[b] = E->buf_lo[b] = nullptr;
+            CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&E->buf_hi[b]), bytes));
+            CUDA_TRY(cudaMemset(E->buf_hi[b], 0, bytes));
+            if (E->exact) {
+                CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&E->buf_lo[b]), bytes));
+                CUDA_TRY(cudaMemset(E->buf_lo[b], 0, bytes));
+            }
+            E->buf_cap[b] = bytes;
+        }
+    }
+    const size_t rbytes = static_cast<size_t>(B) * (H >> 2) * (W >> 2) * E->cfg.filters[2] * sizeof(float);
+    if (E->cfg.resnet_blocks > 0 && rbytes > E->resid_cap) {
+        if (E->resid) cudaFree(E->resid);
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&E->resid), rbytes));
+        E->resid_cap = rbytes;
+    }
+    if (E->cfg.kind == DSU_KIND_GENERATORJ_RIC)
+        for (int l = 0; l < 3; ++l) {
+            int rc = build_level(E, E->lv[l], H >> l, W >> l);
+            if (rc) return rc;
+        }
+    E->B = B; E->H = H; E->W = W;
+    return DSU_OK;
+}
+
+int pick_stages(int a_bytes, int b_bytes, bool pair) {
+    const int stage = a_bytes + b_bytes;
+    int s = (108 * 1024) / stage;          // two CTAs per SM when possible
+    if (s < 2) s = (216 * 1024) / stage;
+    if (pair) s &= ~1;
+    return std::max(2, std::min(kMaxStages, s));
+}
+
+int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgba, const uint8_t* alpha_src,
+                int alpha_stride, cudaStream_t st) {
+    for (const Step& sp : E->steps) {
+        if (sp.type == 1) {
+            const int l = E->buf_level[sp.src];
+            CUDA_TRY(maxpool2(E->buf_hi[sp.src], E->buf_lo[sp.src], E->buf_C[sp.src], sp.src_choff, B, H >> l, W >> l, sp.C,
+                              E->buf_hi[sp.dst], E->buf_lo[sp.dst], E->buf_C[sp.dst], st));
+            continue;
+        }
+        const LayerDef& L = E->layers[sp.layer];
+        ConvParams p{};
+        p.B = B; p.Hout = H >> L.level_out; p.Wout = W >> L.level_out;
+        const int src_level = E->buf_level[L.segs[0].buf];
+        p.Hin = H >> src_level; p.Win = W >> src_level;
+        p.up = L.up; p.Hv = p.Hin << L.up; p.Wv = p.Win << L.up;
+        p.stride = L.stride; p.ric = L.ric; p.exact = E->exact ? 1 : 0;
+        p.nchunks = L.nchunks; p.Cout = L.cout;
+        p.a_bytes = kTileM * 128;
+        p.b_bytes = (E->exact ? 2 : 1) * L.cout * 128;
+        p.nstages = pick_stages(p.a_bytes, p.b_bytes, E->exact && L.ric);
+        int cols = 32;
+        while (cols < (E->exact ? 2 : 1) * L.cout) cols *= 2;
+        p.tmem_cols = cols;
+        p.slots = L.d_slots; p.hdrs = L.d_hdrs; p.wpack = L.d_wpack;
+        for (size_t i = 0; i < L.segs.size(); ++i) {
+            p.seg[i].ptr = E->buf_hi[L.segs[i].buf];
+            p.seg[i].pitch = E->buf_C[L.segs[i].buf];
+            p.seg[i + kMaxSeg / 2].ptr = E->buf_lo[L.segs[i].buf];
+            p.seg[i + kMaxSeg / 2].pitch = E->buf_C[L.segs[i].buf];
+        }
+        if (L.ric) { p.ric_w = E->lv[L.level_out].w4; p.ric_off = E->lv[L.level_out].off; }
+        EpiParams& e = p.epi;
+        e.scale = L.d_scale; e.shift = L.d_shift; e.scale2 = L.d_scale2; e.shift2 = L.d_shift2;
+        e.act = L.act; e.resid_in = L.resid_in; e.resid_out = L.resid_out; e.resid = E->resid;
+        if (L.out_buf >= 0) {
+            e.out_hi = E->buf_hi[L.out_buf]; e.out_lo = E->buf_lo[L.out_buf];
+            e.out_pitch = E->buf_C[L.out_buf]; e.out_choff = L.out_choff; e.out_relu = L.out_relu;
+        }
+        if (L.out2_buf >= 0) {
+            e.out2_hi = E->buf_hi[L.out2_buf]; e.out2_lo = E->buf_lo[L.out2_buf];
+            e.out2_pitch = E->buf_C[L.out2_buf]; e.out2_choff = 0;
+        }
+        if (L.final) {
+            e.w12 = E->d_w12; e.b12 = E->d_b12; e.tanh_flag = E->cfg.tanh;
+            e.y_nchw = y_dev; e.y_rgba = y_rgba; e.alpha_src = alpha_src; e.alpha_stride = alpha_stride;
+        }
+        CUDA_TRY(launch_conv(p, st));
+    }
+    return DSU_OK;
+}
+
+int check_ready(dsu_handle h) {
+    if (!h) return fail(DSU_E_INVALID, "null handle");
+    if (!h->finalized) return fail(DSU_E_STATE, "dsu_finalize has not been called (weights not packed)");
+    return DSU_OK;
+}
+
+}  // namespace
+
+// =================================================================== C ABI
+extern "C" {
+
+const char* dsu_last_error(void) { return g_err.c_str(); }
+const char* dsu_version(void) { return "dsu_b200 0.1 (sm_100a, tcgen05)"; }
+
+int dsu_create(const dsu_config* cfg, dsu_handle* out) {
+    if (!cfg || !out) return fail(DSU_E_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->kind != DSU_KIND_GENERATORJ_RIC && cfg->kind != DSU_KIND_GENERATORJ)
+        return fail(DSU_E_INVALID, "kind must be DSU_KIND_GENERATORJ_RIC or DSU_KIND_GENERATORJ");
+    if (cfg->norm == DSU_NORM_INSTANCE)
+        return fail(DSU_E_NOTIMPL, "norm_layer='instance_norm' (models.py:34-35) is not implemented; no shipped config uses it");
+    if (cfg->norm != DSU_NORM_BATCH && cfg->norm != DSU_NORM_NONE) return fail(DSU_E_INVALID, "bad norm");
+    if (cfg->precision != DSU_PREC_FP16 && cfg->precision != DSU_PREC_FP16X3) return fail(DSU_E_INVALID, "bad precision");
+    if (cfg->input_channels < 1 || cfg->input_channels > 16) return fail(DSU_E_INVALID, "input_channels must be in [1,16]");
+    if (cfg->resnet_blocks < 0 || cfg->resnet_blocks > 64) return fail(DSU_E_INVALID, "resnet_blocks out of range");
+    const int cmax = cfg->precision == DSU_PREC_FP16X3 ? 128 : 256;
+    for (int i = 0; i < 6; ++i)
+        if (cfg->filters[i] < 32 || cfg->filters[i] > cmax || (cfg->filters[i] % 32))
+            return fail(DSU_E_INVALID, "filters must be multiples of 32 in [32," + std::to_string(cmax) + "]");
+    if (cfg->filters[3] != cfg->filters[2])
+        return fail(DSU_E_INVALID, "filters[3] must equal filters[2] (upconv2 concatenates the residual trunk, models.py:72)");
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(DSU_E_INVALID, "no such CUDA device");
+    cudaDeviceProp prop{};
+    CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10)
+        return fail(DSU_E_INVALID, std::string("device '") + prop.name + "' is not sm_100 (tcgen05 kernels only, no fallback path)");
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    dsu_engine* E = new dsu_engine();
+    E->cfg = *cfg;
+    E->cin_pad = (cfg->input_channels + 7) / 8 * 8;
+    E->exact = cfg->precision == DSU_PREC_FP16X3;
+    int rc = build_plan(E);
+    if (rc) { delete E; return rc; }
+    *out = E;
+    return DSU_OK;
+}
+
+void dsu_destroy(dsu_handle h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    for (LayerDef& L : h->layers) {
+        cudaFree(L.d_slots); cudaFree(L.d_hdrs); cudaFree(L.d_wpack);
+        cudaFree(L.d_scale); cudaFree(L.d_shift); cudaFree(L.d_scale2); cudaFree(L.d_shift2);
+    }
+    for (int b = 0; b < NBUF; ++b) { cudaFree(h->buf_hi[b]); cudaFree(h->buf_lo[b]); }
+    for (int l = 0; l < 3; ++l) { cudaFree(h->lv[l].w4); cudaFree(h->lv[l].off); }
+    cudaFree(h->resid); cudaFree(h->d_w12); cudaFree(h->d_b12);
+    cudaFree(h->io_color); cudaFree(h->io_pos); cudaFree(h->io_edge); cudaFree(h->io_out);
+    delete h;
+}
+
+int dsu_expected_keys(dsu_handle h) { return h ? static_cast<int>(h->expected.size()) : 0; }
+int dsu_loaded_keys(dsu_handle h) { return h ? static_cast<int>(h->loaded.size()) : 0; }
+
+int dsu_load_weights(dsu_handle h, const char* key, const void* data, const int64_t* shape, int32_t ndim,
+                     int32_t dtype, int32_t location) {
+    if (!h || !key || !data) return fail(DSU_E_INVALID, "null argument");
+    auto it = h->expected.find(key);
+    if (it == h->expected.end()) return fail(DSU_E_INVALID, std::string("unexpected key in state_dict: ") + key);
+    const std::vector<int64_t>& es = it->second;
+    bool same = static_cast<size_t>(ndim) == es.size();
+    size_t n = 1;
+    for (int i = 0; same && i < ndim; ++i) { same = shape[i] == es[i]; n *= static_cast<size_t>(es[i]); }
+    if (!same) return fail(DSU_E_INVALID, std::string("size mismatch for ") + key);
+    h->finalized = false;
+    if (dtype == 1) { h->loaded.insert(key); return DSU_OK; }   // num_batches_tracked: accepted, unused in eval
+    if (dtype != 0) return fail(DSU_E_INVALID, "dtype must be 0 (float32) or 1 (int64)");
+    std::vector<float>& dst = h->w[key];
+    dst.resize(n);
+    if (location == 1) {
+        CUDA_TRY(cudaSetDevice(h->cfg.device));
+        CUDA_TRY(cudaMemcpy(dst.data(), data, n * sizeof(float), cudaMemcpyDeviceToHost));
+    } else {
+        std::memcpy(dst.data(), data, n * sizeof(float));
+    }
+    h->loaded.insert(key);
+    return DSU_OK;
+}
+
+int dsu_finalize(dsu_handle h, void* stream) {
+    (void)stream;
+    if (!h) return fail(DSU_E_INVALID, "null handle");
+    for (const std::string& k : h->expected_order)
+        if (!h->loaded.count(k)) return fail(DSU_E_STATE, "missing key in state_dict: " + k);
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    for (LayerDef& L : h->layers) {
+        int rc = compile_layer(h, L);
+        if (rc) return rc;
+    }
+    const std::string p12 = conv12_prefix(h->cfg);
+    int rc;
+    if ((rc = upload(&h->d_w12, h->w.at(p12 + ".weight")))) return rc;
+    if ((rc = upload(&h->d_b12, h->w.at(p12 + ".bias")))) return rc;
+    h->finalized = true;
+    return DSU_OK;
+}
+
+int dsu_set_ric_offsets(dsu_handle h, int32_t height, int32_t width, const float* offsets_host) {
+    if (!h || !offsets_host || height <= 0 || width <= 0) return fail(DSU_E_INVALID, "bad argument");
+    h->user_offsets[{height, width}] = std::vector<float>(offsets_host, offsets_host + static_cast<size_t>(18) * height * width);
+    for (int l = 0; l < 3; ++l)
+        if (h->lv[l].h == height && h->lv[l].w == width) h->lv[l].h = h->lv[l].w = 0;   // rebuild on next forward
+    return DSU_OK;
+}
+
+int dsu_forward(dsu_handle h, const float* x_dev, int32_t B, int32_t H, int32_t W, float* y_dev, void* stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!x_dev || !y_dev) return fail(DSU_E_INVALID, "null tensor pointer");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if ((rc = ensure_shape(h, B, H, W))) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(ingest_f32(x_dev, B, h->cfg.input_channels, h->cin_pad, H, W, h->buf_hi[SK0], h->buf_lo[SK0],
+                        h->buf_C[SK0], h->cfg.filters[0], st));
+    return run_network(h, B, H, W, y_dev, nullptr, nullptr, 0, st);
+}
+
+int dsu_forward_u8(dsu_handle h, const uint8_t* color_dev, const uint8_t* pos_dev, const uint8_t* edge_dev,
+                   int32_t B, int32_t H, int32_t W, uint8_t* out_rgba_dev, float* y_dev, void* stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!color_dev || !pos_dev || !out_rgba_dev) return fail(DSU_E_INVALID, "null frame pointer");
+    if (h->cfg.input_channels != 6)
+        return fail(DSU_E_INVALID, "the fused uint8 frame path needs input_channels == 6 (RGB + mask + posXY, test_stage1.py:33-39)");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if ((rc = ensure_shape(h, B, H, W))) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(ingest_u8(color_dev, pos_dev, edge_dev, B, H, W, h->buf_hi[SK0], h->buf_lo[SK0], h->buf_C[SK0],
+                       h->cfg.filters[0], st));
+    return run_network(h, B, H, W, y_dev, out_rgba_dev, color_dev + 3, 4, st);
+}
+
+int dsu_forward_u8_host(dsu_handle h, const uint8_t* color_host, const uint8_t* pos_host, const uint8_t* edge_host,
+                        int32_t B, int32_t H, int32_t W, uint8_t* out_rgba_host, void* stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!color_host || !pos_host || !out_rgba_host) return fail(DSU_E_INVALID, "null frame pointer");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const size_t np = static_cast<size_t>(B) * H * W;
+    if (np * 4 > h->io_cap) {
+        cudaFree(h->io_color); cudaFree(h->io_pos); cudaFree(h->io_edge); cudaFree(h->io_out);
+        h->io_color = h->io_pos = h->io_edge = h->io_out = nullptr; h->io_cap = 0;
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->io_color), np * 4));
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->io_pos), np * 4));
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->io_edge), np));
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->io_out), np * 4));
+        h->io_cap = np * 4;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaMemcpyAsync(h->io_color, color_host, np * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->io_pos, pos_host, np * 4, cudaMemcpyHostToDevice, st));
+    if (edge_host) CUDA_TRY(cudaMemcpyAsync(h->io_edge, edge_host, np, cudaMemcpyHostToDevice, st));
+    rc = dsu_forward_u8(h, h->io_color, h->io_pos, edge_host ? h->io_edge : nullptr, B, H, W, h->io_out, nullptr, stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_rgba_host, h->io_out, np * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return DSU_OK;
+}
+
+size_t dsu_workspace_bytes(dsu_handle h, int32_t B, int32_t H, int32_t W) {
+    if (!h) return 0;
+    size_t total = 0;
+    for (int b = 0; b < NBUF; ++b)
+        if (h->buf_used[b])
+            total += static_cast<size_t>(B) * (H >> h->buf_level[b]) * (W >> h->buf_level[b]) * h->buf_C[b] * 2 * (h->exact ? 2 : 1);
+    if (h->cfg.resnet_blocks > 0) total += static_cast<size_t>(B) * (H >> 2) * (W >> 2) * h->cfg.filters[2] * 4;
+    if (h->cfg.kind == DSU_KIND_GENERATORJ_RIC)
+        for (int l = 0; l < 3; ++l) total += static_cast<size_t>(H >> l) * (W >> l) * 8 * 20;
+    return total;
+}
+
+int dsu_forward_launches(dsu_handle h, int32_t B, int32_t H, int32_t W) {
+    (void)B; (void)H; (void)W;
+    return h ? static_cast<int>(h->steps.size()) + 1 : 0;
+}
+
+double dsu_forward_flops(dsu_handle h, int32_t B, int32_t H, int32_t W) {
+    if (!h) return 0;
+    double macs = 0;
+    for (const LayerDef& L : h->layers) {
+        double mp = L.macs_per_px;
+        if (mp == 0) {   // before finalize: derive from the plan
+            double kk = 0;
+            for (const SegDef& s : L.segs) kk += s.wn;
+            mp = kk * L.k * L.k * L.cout;
+        }
+        macs += mp * static_cast<double>(H >> L.level_out) * (W >> L.level_out);
+    }
+    macs += 3.0 * h->cfg.filters[5] * static_cast<double>(H) * W;   // conv_12
+    return 2.0 * macs * B;
+}
+
+int dsu_frames_to_tensor(const uint8_t* color_dev, const uint8_t* pos_dev, const uint8_t* edge_dev,
+                         int32_t B, int32_t H, int32_t W, float* pre_dev, float* mask_dev, void* stream) {
+    if (!color_dev || !pos_dev || !pre_dev || B <= 0 || H <= 0 || W <= 0) return fail(DSU_E_INVALID, "bad argument");
+    CUDA_TRY(frames_to_tensor(color_dev, pos_dev, edge_dev, B, H, W, pre_dev, mask_dev, static_cast<cudaStream_t>(stream)));
+    return DSU_OK;
+}
+int dsu_to_image_space(const float* x_dev, uint8_t* out_dev, size_t n, void* stream) {
+    if (!x_dev || !out_dev) return fail(DSU_E_INVALID, "null pointer");
+    if (n) CUDA_TRY(to_image_space(x_dev, out_dev, n, static_cast<cudaStream_t>(stream)));
+    return DSU_OK;
+}
+int dsu_overlap_edge(const uint8_t* edge_dev, uint8_t* rgba_dev, size_t npixels, void* stream) {
+    if (!edge_dev || !rgba_dev) return fail(DSU_E_INVALID, "null pointer");
+    if (npixels) CUDA_TRY(overlap_edge(edge_dev, rgba_dev, npixels, static_cast<cudaStream_t>(stream)));
+    return DSU_OK;
+}
+int dsu_compose_rgba(const float* y_dev, const float* mask_dev, int32_t B, int32_t H, int32_t W,
+                     uint8_t* out_rgba_dev, void* stream) {
+    if (!y_dev || !mask_dev || !out_rgba_dev || B <= 0 || H <= 0 || W <= 0) return fail(DSU_E_INVALID, "bad argument");
+    CUDA_TRY(compose_rgba(y_dev, mask_dev, B, H, W, out_rgba_dev, static_cast<cudaStream_t>(stream)));
+    return DSU_OK;
+}
+int dsu_pos2edge(const uint8_t* pos_dev, int32_t B, int32_t H, int32_t W, uint8_t* edge_dev, void* stream) {
+    if (!pos_dev || !edge_dev || B <= 0 || H <= 0 || W <= 0) return fail(DSU_E_INVALID, "bad argument");
+    CUDA_TRY(pos2edge(pos_dev, B, H, W, edge_dev, static_cast<cudaStream_t>(stream)));
+    return DSU_OK;
+}
+
+int dsu_debug_read(dsu_handle h, int32_t buffer, int32_t plane, void* dst_host, size_t bytes) {
+    if (!h || !dst_host) return fail(DSU_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    const void* src = nullptr;
+    size_t have = 0;
+    if (buffer == 100) { src = h->resid; have = h->resid_cap; }
+    else if (buffer >= 0 && buffer < NBUF) { src = plane ? h->buf_lo[buffer] : h->buf_hi[buffer]; have = h->buf_cap[buffer]; }
+    if (!src) return fail(DSU_E_INVALID, "no such buffer in this configuration");
+    CUDA_TRY(cudaMemcpy(dst_host, src, std::min(bytes, have), cudaMemcpyDeviceToHost));
+    return DSU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,232 @@
+// HBM-bound per-pixel kernels around the convolution stack: frame ingest (uint8 / fp32 -> fp16 NHWC
+// hi[/lo] planes), 2x2 max-pool, and the stand-alone uint8 steps of the reference's frame loop
+// (custom_transforms.py:7-35, data.py:23-47, test_stage1.py:68-70, run_render.py:31-57).
+// One thread per pixel (or per 8-channel group), 128-bit accesses where the layout allows.
+#include "frames.cuh"
+
+namespace dsu {
+
+namespace {
+
+__device__ __forceinline__ uint32_t pack_h2f(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// write 8 fp32 values as fp16 hi (and optional lo = fp16(v - hi)) 16-byte groups
+__device__ __forceinline__ void store8(__half* hi, __half* lo, const float* v) {
+    uint4 h;
+    h.x = pack_h2f(v[0], v[1]); h.y = pack_h2f(v[2], v[3]); h.z = pack_h2f(v[4], v[5]); h.w = pack_h2f(v[6], v[7]);
+    *reinterpret_cast<uint4*>(hi) = h;
+    if (lo) {
+        const __half2* hh = reinterpret_cast<const __half2*>(&h);
+        float r[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { float2 t = __half22float2(hh[i]); r[2 * i] = t.x; r[2 * i + 1] = t.y; }
+        uint4 l;
+        l.x = pack_h2f(v[0] - r[0], v[1] - r[1]); l.y = pack_h2f(v[2] - r[2], v[3] - r[3]);
+        l.z = pack_h2f(v[4] - r[4], v[5] - r[5]); l.w = pack_h2f(v[6] - r[6], v[7] - r[7]);
+        *reinterpret_cast<uint4*>(lo) = l;
+    }
+}
+
+// ToTensor + Normalize(0.5, 0.5) of custom_transforms.py:18-22: (u8/255 - 0.5)/0.5, fp32 ops in order
+__device__ __forceinline__ float norm_u8(uint8_t v) {
+    return __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(v), 255.0f), 0.5f), 0.5f);
+}
+
+__global__ void ingest_f32_kernel(const float* __restrict__ x, int cin, int cpad, size_t npix_frame, size_t npix,
+                                  __half* hi, __half* lo, int pitch, int choff) {
+    const size_t p = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (p >= npix) return;
+    const size_t n = p / npix_frame, q = p % npix_frame;
+    const float* xp = x + n * cin * npix_frame + q;
+    for (int g = 0; g < cpad; g += 8) {
+        float v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = (g + c < cin) ? xp[static_cast<size_t>(g + c) * npix_frame] : 0.0f;
+        store8(hi + p * pitch + choff + g, lo ? lo + p * pitch + choff + g : nullptr, v);
+    }
+}
+
+__global__ void ingest_u8_kernel(const uchar4* __restrict__ color, const uchar4* __restrict__ pos,
+                                 const uint8_t* __restrict__ edge, size_t npix,
+                                 __half* hi, __half* lo, int pitch, int choff) {
+    const size_t p = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (p >= npix) return;
+    uchar4 c = color[p];
+    const uchar4 q = pos[p];
+    const float mask = __fdiv_rn(static_cast<float>(c.w), 255.0f);      // alpha BEFORE the edge burn-in (data.py:28)
+    if (edge && edge[p] < 255) { c.x = 0; c.y = 0; c.z = 0; }           // overlap_edge_on_img
+    float v[8] = {norm_u8(c.x), norm_u8(c.y), norm_u8(c.z), mask, norm_u8(q.x), norm_u8(q.y), 0.0f, 0.0f};
+    store8(hi + p * pitch + choff, lo ? lo + p * pitch + choff : nullptr, v);
+}
+
+__global__ void frames_to_tensor_kernel(const uchar4* __restrict__ color, const uchar4* __restrict__ pos,
+                                        const uint8_t* __restrict__ edge, size_t npix_frame, size_t npix,
+                                        float* __restrict__ pre, float* __restrict__ mask_out) {
+    const size_t p = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (p >= npix) return;
+    const size_t n = p / npix_frame, r = p % npix_frame;
+    uchar4 c = color[p];
+    const uchar4 q = pos[p];
+    const float mask = __fdiv_rn(static_cast<float>(c.w), 255.0f);
+    if (edge && edge[p] < 255) { c.x = 0; c.y = 0; c.z = 0; }
+    float* o = pre + n * 6 * npix_frame + r;
+    o[0] = norm_u8(c.x); o[npix_frame] = norm_u8(c.y); o[2 * npix_frame] = norm_u8(c.z);
+    o[3 * npix_frame] = mask; o[4 * npix_frame] = norm_u8(q.x); o[5 * npix_frame] = norm_u8(q.y);
+    if (mask_out) mask_out[p] = mask;
+}
+
+// 2x2 / stride 2 max-pool over NHWC fp16 (8 channels per thread).  With a lo plane the winner is
+// chosen on hi+lo and carries its own (hi, lo) pair.
+__global__ void maxpool2_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo, int in_pitch, int in_choff,
+                                int B, int Hin, int Win, int C,
+                                __half* out_hi, __half* out_lo, int out_pitch) {
+    const int Ho = Hin / 2, Wo = Win / 2, G = C / 8;
+    const size_t total = static_cast<size_t>(B) * Ho * Wo * G;
+    const size_t t = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (t >= total) return;
+    const int g = static_cast<int>(t % G);
+    const size_t op = t / G;
+    const int ox = static_cast<int>(op % Wo);
+    const int oy = static_cast<int>((op / Wo) % Ho);
+    const int n = static_cast<int>(op / (static_cast<size_t>(Wo) * Ho));
+    float best[8], bh[8], bl[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const size_t ip = (static_cast<size_t>(n) * Hin + 2 * oy + (k >> 1)) * Win + 2 * ox + (k & 1);
+        const uint4 rh = *reinterpret_cast<const uint4*>(in_hi + ip * in_pitch + in_choff + g * 8);
+        uint4 rl = make_uint4(0, 0, 0, 0);
+        if (in_lo) rl = *reinterpret_cast<const uint4*>(in_lo + ip * in_pitch + in_choff + g * 8);
+        const __half2* ph = reinterpret_cast<const __half2*>(&rh);
+        const __half2* pl = reinterpret_cast<const __half2*>(&rl);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float2 h2 = __half22float2(ph[c]);
+            const float2 l2 = __half22float2(pl[c]);
+            const float v0 = h2.x + l2.x, v1 = h2.y + l2.y;
+            if (k == 0 || v0 > best[2 * c]) { best[2 * c] = v0; bh[2 * c] = h2.x; bl[2 * c] = l2.x; }
+            if (k == 0 || v1 > best[2 * c + 1]) { best[2 * c + 1] = v1; bh[2 * c + 1] = h2.y; bl[2 * c + 1] = l2.y; }
+        }
+    }
+    uint4 oh, ol;
+    oh.x = pack_h2f(bh[0], bh[1]); oh.y = pack_h2f(bh[2], bh[3]); oh.z = pack_h2f(bh[4], bh[5]); oh.w = pack_h2f(bh[6], bh[7]);
+    *reinterpret_cast<uint4*>(out_hi + op * out_pitch + g * 8) = oh;
+    if (out_lo) {
+        ol.x = pack_h2f(bl[0], bl[1]); ol.y = pack_h2f(bl[2], bl[3]); ol.z = pack_h2f(bl[4], bl[5]); ol.w = pack_h2f(bl[6], bl[7]);
+        *reinterpret_cast<uint4*>(out_lo + op * out_pitch + g * 8) = ol;
+    }
+}
+
+__device__ __forceinline__ uint8_t to_u8_dev(float x) {
+    x = fminf(fmaxf(x, -1.0f), 1.0f);
+    const float t = __fmul_rn(__fmul_rn(__fadd_rn(x, 1.0f), 0.5f), 255.0f);
+    return static_cast<uint8_t>(static_cast<int>(t));
+}
+
+__global__ void to_image_space_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, size_t n) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i < n) out[i] = to_u8_dev(x[i]);
+}
+
+__global__ void overlap_edge_kernel(const uint8_t* __restrict__ edge, uchar4* rgba, size_t npix) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i < npix && edge[i] < 255) rgba[i] = make_uchar4(0, 0, 0, 255);
+}
+
+__global__ void compose_rgba_kernel(const float* __restrict__ y, const float* __restrict__ mask,
+                                    size_t npix_frame, size_t npix, uchar4* __restrict__ out) {
+    const size_t p = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (p >= npix) return;
+    const size_t n = p / npix_frame, r = p % npix_frame;
+    const float* yp = y + n * 3 * npix_frame + r;
+    const uint8_t a = static_cast<uint8_t>(static_cast<int>(__fmul_rn(mask[p], 255.0f)));   // (mask*255).astype(uint8)
+    out[p] = make_uchar4(to_u8_dev(yp[0]), to_u8_dev(yp[npix_frame]), to_u8_dev(yp[2 * npix_frame]), a);
+}
+
+// pos2edge (run_render.py:31-57): per channel Sobel-3 (BORDER_REFLECT_101) in float64 on u8/255 with
+// the background (alpha < 255) forced to 2, max magnitude over the 3 channels > 0.3.
+__global__ void pos2edge_kernel(const uchar4* __restrict__ pos, int B, int H, int W, uint8_t* __restrict__ edge) {
+    const size_t p = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    const size_t npf = static_cast<size_t>(H) * W;
+    if (p >= npf * B) return;
+    const int x = static_cast<int>(p % W);
+    const int y = static_cast<int>((p / W) % H);
+    const uchar4* f = pos + (p / npf) * npf;
+    double v[3][3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        int yy = y + i - 1;
+        yy = yy < 0 ? -yy : (yy >= H ? 2 * H - 2 - yy : yy);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            int xx = x + j - 1;
+            xx = xx < 0 ? -xx : (xx >= W ? 2 * W - 2 - xx : xx);
+            const uchar4 q = f[static_cast<size_t>(yy) * W + xx];
+            const bool bg = q.w < 255;
+            v[0][i][j] = bg ? 2.0 : static_cast<double>(__fdiv_rn(static_cast<float>(q.x), 255.0f));
+            v[1][i][j] = bg ? 2.0 : static_cast<double>(__fdiv_rn(static_cast<float>(q.y), 255.0f));
+            v[2][i][j] = bg ? 2.0 : static_cast<double>(__fdiv_rn(static_cast<float>(q.z), 255.0f));
+        }
+    }
+    double best = 0.0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const double gx = (v[c][0][2] - v[c][0][0]) + 2.0 * (v[c][1][2] - v[c][1][0]) + (v[c][2][2] - v[c][2][0]);
+        const double gy = (v[c][2][0] - v[c][0][0]) + 2.0 * (v[c][2][1] - v[c][0][1]) + (v[c][2][2] - v[c][0][2]);
+        best = fmax(best, sqrt(gx * gx + gy * gy));
+    }
+    edge[p] = best > 0.3 ? 255 : 0;
+}
+
+inline unsigned blocks_for(size_t n, int threads) { return static_cast<unsigned>((n + threads - 1) / threads); }
+
+}  // namespace
+
+cudaError_t ingest_f32(const float* x, int B, int cin, int cpad, int H, int W, __half* hi, __half* lo, int pitch,
+                       int choff, cudaStream_t st) {
+    const size_t npf = static_cast<size_t>(H) * W, np = npf * B;
+    ingest_f32_kernel<<<blocks_for(np, 256), 256, 0, st>>>(x, cin, cpad, npf, np, hi, lo, pitch, choff);
+    return cudaGetLastError();
+}
+cudaError_t ingest_u8(const uint8_t* color, const uint8_t* pos, const uint8_t* edge, int B, int H, int W,
+                      __half* hi, __half* lo, int pitch, int choff, cudaStream_t st) {
+    const size_t np = static_cast<size_t>(H) * W * B;
+    ingest_u8_kernel<<<blocks_for(np, 256), 256, 0, st>>>(reinterpret_cast<const uchar4*>(color),
+                                                          reinterpret_cast<const uchar4*>(pos), edge, np, hi, lo, pitch, choff);
+    return cudaGetLastError();
+}
+cudaError_t frames_to_tensor(const uint8_t* color, const uint8_t* pos, const uint8_t* edge, int B, int H, int W,
+                             float* pre, float* mask, cudaStream_t st) {
+    const size_t npf = static_cast<size_t>(H) * W, np = npf * B;
+    frames_to_tensor_kernel<<<blocks_for(np, 256), 256, 0, st>>>(reinterpret_cast<const uchar4*>(color),
+                                                                 reinterpret_cast<const uchar4*>(pos), edge, npf, np, pre, mask);
+    return cudaGetLastError();
+}
+cudaError_t maxpool2(const __half* in_hi, const __half* in_lo, int in_pitch, int in_choff, int B, int Hin, int Win, int C,
+                     __half* out_hi, __half* out_lo, int out_pitch, cudaStream_t st) {
+    const size_t total = static_cast<size_t>(B) * (Hin / 2) * (Win / 2) * (C / 8);
+    maxpool2_kernel<<<blocks_for(total, 256), 256, 0, st>>>(in_hi, in_lo, in_pitch, in_choff, B, Hin, Win, C, out_hi, out_lo, out_pitch);
+    return cudaGetLastError();
+}
+cudaError_t to_image_space(const float* x, uint8_t* out, size_t n, cudaStream_t st) {
+    to_image_space_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x, out, n);
+    return cudaGetLastError();
+}
+cudaError_t overlap_edge(const uint8_t* edge, uint8_t* rgba, size_t npix, cudaStream_t st) {
+    overlap_edge_kernel<<<blocks_for(npix, 256), 256, 0, st>>>(edge, reinterpret_cast<uchar4*>(rgba), npix);
+    return cudaGetLastError();
+}
+cudaError_t compose_rgba(const float* y, const float* mask, int B, int H, int W, uint8_t* out, cudaStream_t st) {
+    const size_t npf = static_cast<size_t>(H) * W, np = npf * B;
+    compose_rgba_kernel<<<blocks_for(np, 256), 256, 0, st>>>(y, mask, npf, np, reinterpret_cast<uchar4*>(out));
+    return cudaGetLastError();
+}
+cudaError_t pos2edge(const uint8_t* pos, int B, int H, int W, uint8_t* edge, cudaStream_t st) {
+    const size_t np = static_cast<size_t>(H) * W * B;
+    pos2edge_kernel<<<blocks_for(np, 256), 256, 0, st>>>(reinterpret_cast<const uchar4*>(pos), B, H, W, edge);
+    return cudaGetLastError();
+}
+
+}  // namespace dsu

@@ -1,0 +1,22 @@
+// Launch wrappers of the per-pixel frame kernels (frames.cu).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dsu {
+
+cudaError_t ingest_f32(const float* x, int B, int cin, int cpad, int H, int W, __half* hi, __half* lo, int pitch,
+                       int choff, cudaStream_t st);
+cudaError_t ingest_u8(const uint8_t* color, const uint8_t* pos, const uint8_t* edge, int B, int H, int W,
+                      __half* hi, __half* lo, int pitch, int choff, cudaStream_t st);
+cudaError_t frames_to_tensor(const uint8_t* color, const uint8_t* pos, const uint8_t* edge, int B, int H, int W,
+                             float* pre, float* mask, cudaStream_t st);
+cudaError_t maxpool2(const __half* in_hi, const __half* in_lo, int in_pitch, int in_choff, int B, int Hin, int Win, int C,
+                     __half* out_hi, __half* out_lo, int out_pitch, cudaStream_t st);
+cudaError_t to_image_space(const float* x, uint8_t* out, size_t n, cudaStream_t st);
+cudaError_t overlap_edge(const uint8_t* edge, uint8_t* rgba, size_t npix, cudaStream_t st);
+cudaError_t compose_rgba(const float* y, const float* mask, int B, int H, int W, uint8_t* out, cudaStream_t st);
+cudaError_t pos2edge(const uint8_t* pos, int B, int H, int W, uint8_t* edge, cudaStream_t st);
+
+}  // namespace dsu
