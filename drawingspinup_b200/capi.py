@@ -52,6 +52,8 @@ SYMBOLS = {
     "dsu_overlap_edge": (C.c_int, [_VP, _VP, _SZ, _VP]),
     "dsu_compose_rgba": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _VP, _VP]),
     "dsu_pos2edge": (C.c_int, [_VP, _I32, _I32, _I32, _VP, _VP]),
+    "dsu_profile_forward": (C.c_int, [_VP, _I32, _I32, _I32, _I32, _VP, C.POINTER(C.c_double), C.POINTER(C.c_double), _I32]),
+    "dsu_step_name": (C.c_char_p, [_VP, _I32]),
     "dsu_debug_read": (C.c_int, [_VP, _I32, _I32, _VP, _SZ]),
 }
 

@@ -461,8 +461,11 @@ int pick_stages(int a_bytes, int b_bytes, bool pair) {
 }
 
 int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgba, const uint8_t* alpha_src,
-                int alpha_stride, cudaStream_t st) {
+                int alpha_stride, cudaStream_t st, std::vector<cudaEvent_t>* evs = nullptr) {
+    size_t step_idx = 0;
     for (const Step& sp : E->steps) {
+        if (evs) CUDA_TRY(cudaEventRecord((*evs)[step_idx], st));
+        ++step_idx;
         if (sp.type == 1) {
             const int l = E->buf_level[sp.src];
             CUDA_TRY(maxpool2(E->buf_hi[sp.src], E->buf_lo[sp.src], E->buf_C[sp.src], sp.src_choff, B, H >> l, W >> l, sp.C,
@@ -508,6 +511,7 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
         }
         CUDA_TRY(launch_conv(p, st));
     }
+    if (evs) CUDA_TRY(cudaEventRecord((*evs)[step_idx], st));
     return DSU_OK;
 }
 
@@ -713,6 +717,49 @@ double dsu_forward_flops(dsu_handle h, int32_t B, int32_t H, int32_t W) {
     }
     macs += 3.0 * h->cfg.filters[5] * static_cast<double>(H) * W;   // conv_12
     return 2.0 * macs * B;
+}
+
+int dsu_profile_forward(dsu_handle h, int32_t B, int32_t H, int32_t W, int32_t reps, void* stream,
+                        double* ms_out, double* flops_out, int32_t capacity) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!ms_out || !flops_out || reps <= 0) return fail(DSU_E_INVALID, "bad argument");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if ((rc = ensure_shape(h, B, H, W))) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t n = h->steps.size();
+    std::vector<cudaEvent_t> evs(n + 1);
+    for (auto& e : evs) CUDA_TRY(cudaEventCreate(&e));
+    std::vector<double> acc(n, 0.0);
+    for (int r = 0; r < reps; ++r) {
+        if ((rc = run_network(h, B, H, W, nullptr, nullptr, nullptr, 0, st, &evs))) return rc;
+        CUDA_TRY(cudaStreamSynchronize(st));
+        for (size_t i = 0; i < n; ++i) {
+            float ms = 0;
+            CUDA_TRY(cudaEventElapsedTime(&ms, evs[i], evs[i + 1]));
+            acc[i] += ms;
+        }
+    }
+    for (auto& e : evs) cudaEventDestroy(e);
+    for (size_t i = 0; i < n && i < static_cast<size_t>(capacity); ++i) {
+        ms_out[i] = acc[i] / reps;
+        const Step& sp = h->steps[i];
+        if (sp.type == 0) {
+            const LayerDef& L = h->layers[sp.layer];
+            double f = 2.0 * L.macs_per_px * (H >> L.level_out) * (W >> L.level_out) * B;
+            if (L.final) f += 2.0 * 3.0 * L.cout * static_cast<double>(H) * W * B;
+            flops_out[i] = f;
+        } else {
+            flops_out[i] = 0;
+        }
+    }
+    return static_cast<int>(n);
+}
+
+const char* dsu_step_name(dsu_handle h, int32_t index) {
+    if (!h || index < 0 || index >= static_cast<int>(h->steps.size())) return "";
+    const Step& sp = h->steps[index];
+    return sp.type == 0 ? h->layers[sp.layer].name.c_str() : "maxpool";
 }
 
 int dsu_frames_to_tensor(const uint8_t* color_dev, const uint8_t* pos_dev, const uint8_t* edge_dev,

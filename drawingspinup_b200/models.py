@@ -282,6 +282,24 @@ class _Generator(nn.Module):
         dev = torch.device("cuda", self._handle_dev) if self._handle_dev is not None else next(self.parameters()).device
         return int(capi.lib().dsu_forward_launches(self._engine(dev), b, h, w))
 
+    def profile_layers(self, b: int, h: int, w: int, reps: int = 3):
+        """Per-launch device time of one forward of this shape, measured with CUDA events around
+        every launch on the current stream (C ABI ``dsu_profile_forward``).  Returns a list of
+        ``(name, ms, algorithmic_flops)``; run a real forward of the same shape first so the
+        workspace holds meaningful activations."""
+        dev = torch.device("cuda", self._handle_dev)
+        handle = self._engine(dev)
+        self._prepare_shape(h, w)
+        cap = 256
+        ms = (C.c_double * cap)()
+        fl = (C.c_double * cap)()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            n = capi.lib().dsu_profile_forward(handle, b, h, w, reps, C.c_void_p(stream), ms, fl, cap)
+        if n < 0:
+            capi.check(n, "dsu_profile_forward")
+        return [(capi.lib().dsu_step_name(handle, i).decode(), ms[i], fl[i]) for i in range(min(n, cap))]
+
     def debug_buffer(self, buffer: int, plane: int, shape, dtype=torch.float16) -> torch.Tensor:
         """Test hook: host copy of an internal activation buffer (see dsu_debug_read)."""
         t = torch.empty(shape, dtype=dtype)

@@ -108,6 +108,15 @@ size_t dsu_workspace_bytes(dsu_handle h, int32_t B, int32_t H, int32_t W);
 int dsu_forward_launches(dsu_handle h, int32_t B, int32_t H, int32_t W);
 double dsu_forward_flops(dsu_handle h, int32_t B, int32_t H, int32_t W);
 
+/* Measurement hook: re-run the launches of one forward of this shape `reps` times on the current
+ * workspace contents with a CUDA event pair around every launch; ms_out[i] = mean milliseconds of
+ * launch i, flops_out[i] = its algorithmic FLOPs (0 for non-convolution launches).  Returns the
+ * number of launches (<= capacity are written) or a negative error.  Synchronizes the stream. */
+int dsu_profile_forward(dsu_handle h, int32_t B, int32_t H, int32_t W, int32_t reps, void* stream,
+                        double* ms_out, double* flops_out, int32_t capacity);
+/* Name of launch i of a forward ("ingest", "conv0", "maxpool", "resnets.3.conv_1", ...). */
+const char* dsu_step_name(dsu_handle h, int32_t index);
+
 /* ---- stand-alone uint8 / fp32 frame steps (device pointers) -------------------------------- */
 /* DatasetFullImages.__getitem__ (data.py:23-47): pre_dev fp32 [B,6,H,W] = RGB(3) | mask | posXY(2),
  * mask_dev fp32 [B,1,H,W] (may be NULL).  edge_dev NULL = stage 1. */

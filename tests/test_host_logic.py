@@ -1,0 +1,216 @@
+"""CPU: host-side mirror of the reference interface, the C-ABI surface, synthetic data, sharding."""
+import ctypes
+import os
+import re
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import DEFAULT_ARGS, VARIANT_ARGS, ROOT
+import drawingspinup_b200 as dsu
+from drawingspinup_b200 import capi, synth
+from drawingspinup_b200.pipeline import shard_range
+from oracle import reference_port as rp
+
+
+# ---------------------------------------------------------------- state-dict contract
+@pytest.mark.parametrize("stage,cls", [(1, dsu.GeneratorJ_RIC), (2, dsu.GeneratorJ)])
+def test_state_dict_layout_matches_reference(stage, cls):
+    m = cls(**DEFAULT_ARGS)
+    sd = m.state_dict()
+    ref = synth.make_state_dict(stage)
+    assert len(sd) == 89
+    assert list(sd.keys()) == list(ref.keys())
+    for k, v in sd.items():
+        assert tuple(v.shape) == tuple(ref[k].shape), k
+    k0 = 3 if stage == 1 else 7
+    assert tuple(sd["conv0.conv.weight"].shape) == (32, 6, k0, k0)
+    assert tuple(sd["conv_11.0.weight"].shape) == (64, 166, k0, k0)
+    assert sd["conv0.normalization.num_batches_tracked"].dtype == torch.int64
+    assert sum(v.numel() for k, v in sd.items() if v.dtype != torch.int64 and "running" not in k) == \
+        (3279427 if stage == 2 else 3279427 - 32 * 6 * 40 - 64 * 166 * 40)
+
+
+@pytest.mark.parametrize("cls", [dsu.GeneratorJ_RIC, dsu.GeneratorJ])
+def test_strict_load_and_round_trip(cls):
+    stage = 1 if cls is dsu.GeneratorJ_RIC else 2
+    m = cls(**DEFAULT_ARGS)
+    sd = synth.to_torch_state_dict(synth.make_state_dict(stage, seed=5))
+    m.load_state_dict(sd)                               # strict=True
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    bad = dict(sd)
+    bad.pop("conv_12.0.bias")
+    with pytest.raises(RuntimeError):
+        m.load_state_dict(bad)
+    bad = dict(sd)
+    bad["extra.weight"] = torch.zeros(1)
+    with pytest.raises(RuntimeError):
+        m.load_state_dict(bad)
+
+
+def test_reference_constructor_signature_and_defaults():
+    import inspect
+    sig = inspect.signature(dsu.GeneratorJ.__init__)
+    names = list(sig.parameters)[1:9]
+    assert names == ["norm_layer", "gpu_ids", "use_bias", "resnet_blocks", "tanh", "filters", "input_channels", "append_smoothers"]
+    d = {k: sig.parameters[k].default for k in names}
+    assert d == dict(norm_layer="batch_norm", gpu_ids=None, use_bias=False, resnet_blocks=9, tanh=False,
+                     filters=(64, 128, 128, 128, 128, 64), input_channels=3, append_smoothers=False)
+    m = dsu.GeneratorJ()                                # reference defaults: 9 blocks, no tanh, no smoothers
+    assert "conv_12.weight" in m.state_dict() and "conv_11_a.0.weight" not in m.state_dict()
+    assert len([k for k in m.state_dict() if k.startswith("resnets.8.")]) > 0
+
+
+def test_variant_config_keys():
+    m = dsu.GeneratorJ(**VARIANT_ARGS)
+    keys = list(m.state_dict().keys())
+    ref = list(synth.make_state_dict(2, filters=VARIANT_ARGS["filters"], resnet_blocks=2, input_channels=5, tanh=False,
+                                     append_smoothers=False, use_bias=True).keys())
+    assert keys == ref
+
+
+def test_unsupported_options_fail_loudly():
+    with pytest.raises(NotImplementedError):
+        dsu.GeneratorJ(norm_layer="instance_norm")
+    with pytest.raises(AssertionError):
+        dsu.GeneratorJ(norm_layer="layer_norm")
+    with pytest.raises(ValueError):
+        dsu.GeneratorJ(precision="fp8")
+
+
+def test_no_cpu_fallback():
+    m = dsu.GeneratorJ(**DEFAULT_ARGS).eval()
+    with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 6, 16, 16))
+    m.train()
+    with pytest.raises(RuntimeError, match="inference-only"):
+        m(torch.zeros(1, 6, 16, 16))
+
+
+def test_install_rebinds_reference_names():
+    fake = types.ModuleType("training.models")
+    fake.GeneratorJ = object
+    fake.GeneratorJ_RIC = object
+    dsu.install(fake)
+    assert fake.GeneratorJ is dsu.GeneratorJ and fake.GeneratorJ_RIC is dsu.GeneratorJ_RIC
+    # build_model's lookup (trainers.py:33-35): getattr(m, model_type)(**args)
+    model = getattr(fake, "GeneratorJ_RIC")(**DEFAULT_ARGS)
+    assert isinstance(model, dsu.GeneratorJ_RIC)
+
+
+def test_launcher_runs_script_with_rebound_classes(tmp_path, monkeypatch, capsys):
+    """drawingspinup_b200.run on a miniature stand-in for 3_style_translator: the script resolves the
+    class through training.models exactly like trainers.build_model does."""
+    pkg = tmp_path / "training"
+    pkg.mkdir()
+    (pkg / "models.py").write_text("class GeneratorJ: pass\nclass GeneratorJ_RIC: pass\n")
+    (tmp_path / "script.py").write_text(
+        "import sys, training.models as m\n"
+        "g = getattr(m, 'GeneratorJ')(input_channels=6)\n"
+        "print('CLASS', type(g).__module__, len(g.state_dict()), sys.argv[1:])\n")
+    from drawingspinup_b200 import run
+    monkeypatch.setattr(sys, "argv", list(sys.argv))
+    cwd = os.getcwd()
+    for k in [k for k in sys.modules if k == "training" or k.startswith("training.")]:
+        monkeypatch.delitem(sys.modules, k)
+    try:
+        assert run.main([str(tmp_path / "script.py"), "--uid", "abc"]) == 0
+    finally:
+        os.chdir(cwd)
+        for k in [k for k in sys.modules if k == "training" or k.startswith("training.")]:
+            sys.modules.pop(k)
+        if str(tmp_path) in sys.path:
+            sys.path.remove(str(tmp_path))
+    out = capsys.readouterr().out
+    assert "CLASS drawingspinup_b200.models" in out and "['--uid', 'abc']" in out
+
+
+# ---------------------------------------------------------------- RIC offsets: product restatement == oracle == golden
+def test_package_ric_offsets_bit_identical_to_oracle(golden_dir):
+    for h, w in ((24, 20), (16, 16), (33, 12)):
+        assert torch.equal(dsu.ric_offsets(h, w), rp.ric_offsets(h, w))
+    g = np.load(os.path.join(golden_dir, "ric_coords_24x20.npz"))
+    assert np.array_equal(dsu.ric_offsets(24, 20).numpy(), g["coords"])
+
+
+# ---------------------------------------------------------------- C ABI surface
+def _header_functions():
+    text = open(os.path.join(ROOT, "include", "dsu_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dsu_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    lib = ctypes.CDLL(built_lib)
+    names = _header_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), "missing export " + n
+    assert sorted(capi.SYMBOLS) == names                # the ctypes table covers the whole header
+    assert b"sm_100a" in capi.lib().dsu_version()
+
+
+def test_c_abi_rejects_bad_arguments_without_gpu(built_lib):
+    lib = capi.lib()
+    h = ctypes.c_void_p()
+    assert lib.dsu_create(None, ctypes.byref(h)) < 0 and "null" in capi.last_error()
+    cfg = capi.DsuConfig()
+    cfg.kind = 7
+    assert lib.dsu_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
+    cfg.kind = capi.KIND_GENERATORJ
+    cfg.norm = capi.NORM_INSTANCE
+    assert lib.dsu_create(ctypes.byref(cfg), ctypes.byref(h)) == capi.E_NOTIMPL
+    assert lib.dsu_forward(None, None, 1, 16, 16, None, None) < 0
+    assert lib.dsu_to_image_space(None, None, 4, None) < 0
+    lib.dsu_destroy(None)                               # no-op, must not crash
+
+
+def test_missing_library_message(monkeypatch):
+    monkeypatch.setattr(capi, "_lib", None)
+    monkeypatch.setattr(capi, "LIB_PATH", "/nonexistent/libdsu_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
+        capi.lib()
+
+
+# ---------------------------------------------------------------- frame sharding
+@pytest.mark.parametrize("n,world", [(64, 1), (64, 8), (339, 8), (210, 4), (5, 8), (0, 2), (256, 2)])
+def test_shard_ranges_tile_the_sequence(n, world):
+    got = [shard_range(n, r, world) for r in range(world)]
+    assert got[0][0] == 0 and got[-1][1] == n
+    sizes = [hi - lo for lo, hi in got]
+    assert all(a[1] == b[0] for a, b in zip(got, got[1:]))
+    assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(n, world, world)
+
+
+# ---------------------------------------------------------------- synthetic data
+def test_synth_is_deterministic_and_well_formed():
+    a = synth.make_frames(3, 64, 48, seed=3)
+    b = synth.make_frames(3, 64, 48, seed=3)
+    c = synth.make_frames(3, 64, 48, seed=4)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    assert not np.array_equal(a[0], c[0])
+    color, pos, edge = a
+    assert color.shape == (3, 64, 48, 4) and pos.shape == (3, 64, 48, 4) and edge.shape == (3, 64, 48)
+    cover = (color[..., 3] > 0).mean()
+    assert 0.1 < cover < 0.8
+    assert np.all(color[color[..., 3] == 0][:, :3] == 0)
+    assert set(np.unique(edge)) <= {0, 255} and 0 < (edge == 0).mean() < 0.2
+    sd_a, sd_b = synth.make_state_dict(1, seed=8), synth.make_state_dict(1, seed=8)
+    assert all(np.array_equal(sd_a[k], sd_b[k]) for k in sd_a)
+
+
+def test_algorithmic_flop_model_matches_baseline_md():
+    # MAC per full-resolution pixel, stage 1 live = 567552, stage 2 = 1037056
+    def macs(stage):
+        f, cin, k0 = [32, 64, 128, 128, 128, 64], 6, (3 if stage == 1 else 7)
+        m = k0 * k0 * cin * f[0] + 9 * f[0] * f[1] / 4 + 9 * f[1] * f[2] / 16 + 14 * 9 * f[2] * f[2] / 16
+        m += 9 * (f[3] + f[2]) * f[4] / 4 + 9 * (f[4] + f[1]) * f[4] + k0 * k0 * (f[0] + f[4] + cin) * f[5]
+        m += (2 if stage == 2 else 1) * 9 * f[5] * f[5] + 3 * f[5]
+        return m
+    assert macs(1) == 567552 and macs(2) == 1037056
