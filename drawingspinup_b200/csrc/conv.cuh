@@ -6,19 +6,23 @@
 
 namespace dsu {
 
-constexpr int kTileH = 8;      // output patch rows per CTA
-constexpr int kTileW = 16;     // output patch cols per CTA
-constexpr int kTileM = 128;    // = UMMA M
-constexpr int kChunkK = 64;    // fp16 K elements per smem row (128 B, SWIZZLE_128B)
-constexpr int kWorkers = 128;  // producer / epilogue threads (warps 0-3)
-constexpr int kThreads = 192;  // + warp 4 (MMA issue, TMEM alloc) + warp 5 (weight loader)
-constexpr int kMaxSeg = 6;     // concat segments (x2 for the lo planes in exact mode)
-constexpr int kMaxStages = 8;
+constexpr int kTileH = 8;       // output patch rows per CTA
+constexpr int kTileW = 16;      // output patch cols per CTA
+constexpr int kTileM = 128;     // = UMMA M
+constexpr int kChunkK = 64;     // fp16 K elements per smem row (128 B, SWIZZLE_128B)
+constexpr int kABytes = kTileM * 128;   // bytes of one A stage
+constexpr int kWorkers = 256;   // producer / epilogue threads (warps 0-7)
+constexpr int kThreads = 320;   // + warp 8 (MMA issue, TMEM alloc) + warp 9 (weight loader)
+constexpr int kMaxSeg = 6;      // concat segments (second half = lo planes in exact mode)
+constexpr int kMaxStagesA = 9;  // RIC keeps one A buffer per tap resident
+constexpr int kMaxStagesB = 4;
 
-// One 16-byte (8-channel) K slot of a chunk: which tap of which source segment fills it.
+// One 16-byte (8-channel) K slot: which tap of which source segment fills it.
+// plain conv: one entry per (chunk, slot).  RIC conv: one entry per (64-channel block, slot) - the
+// tap is the chunk's position inside the block.
 struct Slot {
-    int8_t dy, dx;      // plain: tap offset (kh - pad, kw - pad).  RIC: dy = raster tap index 0..8
-    uint8_t seg;        // source segment index
+    int8_t dy, dx;      // plain: tap offset (kh - pad, kw - pad)
+    uint8_t seg;        // source segment index (lo plane = seg + kMaxSeg/2)
     uint8_t valid;      // 0 -> zero fill (K padding)
     uint16_t choff;     // first channel inside the segment buffer
     uint16_t pad_;
@@ -27,10 +31,10 @@ static_assert(sizeof(Slot) == 8, "Slot must be 8 bytes");
 
 // One K chunk (8 slots = 64 K elements) of the implicit GEMM.
 struct ChunkHdr {
-    uint8_t ksteps;     // UMMA K=16 steps actually issued (1..4)
-    uint8_t wide;       // 1: B tile holds [W_hi ; W_lo] (N = 2*Cout) - exact-mode hi-plane chunk
+    uint8_t kmask;      // which of the 4 UMMA K=16 steps are issued against B tile 0
+    uint8_t kmask2;     // exact mode: which of steps 0-1 (the hi half) are issued against B tile 1 (W_lo)
     uint16_t pad_;
-    uint32_t b_off;     // byte offset of this chunk's B tile inside wpack
+    uint32_t b_off;     // byte offset of this chunk's B tile(s) inside wpack
 };
 static_assert(sizeof(ChunkHdr) == 8, "ChunkHdr must be 8 bytes");
 
@@ -40,8 +44,6 @@ struct Seg {
     int pad_;
 };
 
-// Per bilinear stencil entry of a RIC level: weights of the 4 corners (invalid corners already 0)
-// and the CLAMPED corner offsets relative to the output pixel {dy_lo, dy_hi, dx_lo, dx_hi}.
 struct EpiParams {
     const float* scale;     // [Cout] pre-activation affine (folded BN / bias); never null
     const float* shift;
@@ -71,14 +73,16 @@ struct ConvParams {
     int Hin, Win;           // source buffer geometry (before the fused nearest x2)
     int Hv, Wv;             // virtual conv-input geometry = (Hin << up, Win << up)
     int stride, up, ric, exact;
-    int nchunks, Cout, nstages, tmem_cols;
-    int a_bytes, b_bytes;   // bytes per A / B stage
-    const Slot* slots;      // [nchunks][8]
+    int nchunks, nblocks, Cout, sa, sb, tmem_cols;
+    int b_bytes;            // bytes per B stage
+    const Slot* slots;      // plain: [nchunks][8]; RIC: [nblocks][8]
     const ChunkHdr* hdrs;   // [nchunks]
     const uint8_t* wpack;   // pre-swizzled B tiles
     Seg seg[kMaxSeg];
-    const float4* ric_w;    // [8][Hout*Wout]
-    const char4* ric_off;   // [8][Hout*Wout]
+    // RIC stencil of the output level, per pixel: octant (tap rotation) and, in rotated tap
+    // order m = (octant + k) & 7, the bilinear fractions (ly, lx) relative to the static quadrant of m
+    const float2* ric_lyx;  // [Hout*Wout][8]
+    const uint8_t* ric_oct; // [Hout*Wout]
     EpiParams epi;
 };
 

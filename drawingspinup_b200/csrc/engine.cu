@@ -54,7 +54,7 @@ struct LayerDef {
     int out_buf = -1, out_choff = 0, out_relu = 0, out2_buf = -1;
     int resid_in = 0, resid_out = 0, final = 0;
     // compiled at finalize
-    int nchunks = 0;
+    int nchunks = 0, nblocks = 0;
     Slot* d_slots = nullptr;
     ChunkHdr* d_hdrs = nullptr;
     uint8_t* d_wpack = nullptr;
@@ -70,8 +70,9 @@ struct Step {
 
 struct Level {
     int h = 0, w = 0;
-    float4* w4 = nullptr;
-    char4* off = nullptr;
+    float2* lyx = nullptr;    // [h*w][8] bilinear fractions in rotated tap order
+    uint8_t* oct = nullptr;   // [h*w] octant (tap rotation) of the pixel
+    float max_clamp = 0;      // largest adjustment needed to express a tap in its static quadrant
 };
 
 }  // namespace
@@ -260,64 +261,99 @@ int compile_layer(dsu_engine* E, LayerDef& L) {
     for (const SegDef& s : L.segs) cin_total = std::max(cin_total, s.wch0 + s.wn);
     if (Wt.size() != static_cast<size_t>(C) * cin_total * k * k) return fail(DSU_E_INVALID, "weight size mismatch for " + L.wkey);
 
+    // A "data slot" is 8 input channels of one concat segment at one tap.  A chunk (8 smem slots =
+    // 64 K elements) holds 8 data slots (fp16 mode) or 4 data slots as [hi x4 | lo x4] (exact mode).
+    // plain conv: data slots are packed densely over (tap, segment, channel group);
+    // RIC conv: channel groups are packed into blocks and every block spans the 9 taps (one chunk each).
     struct HSlot { int kh, kw, seg, choff, wch, nvalid; };
-    std::vector<HSlot> hs;
+    const int dpc = exact ? 4 : 8;            // data slots per chunk
+    std::vector<std::vector<HSlot>> chunks;   // data slots of every chunk, in execution order
+    std::vector<Slot> slots;
     double real_k = 0;
-    for (int kh = 0; kh < k; ++kh)
-        for (int kw = 0; kw < k; ++kw)
-            for (size_t si = 0; si < L.segs.size(); ++si) {
-                const SegDef& s = L.segs[si];
-                for (int c8 = 0; c8 < s.nch; c8 += 8)
-                    hs.push_back(HSlot{kh, kw, (int)si, s.choff + c8, s.wch0 + c8, std::max(0, std::min(8, s.wn - c8))});
-                real_k += s.wn;
-            }
+    for (const SegDef& s : L.segs) real_k += static_cast<double>(s.wn) * k * k;
     L.macs_per_px = real_k * C;
-    const int nlog = static_cast<int>((hs.size() + 7) / 8);
-    const int per = exact ? 2 : 1;
-    L.nchunks = nlog * per;
-    std::vector<Slot> slots(static_cast<size_t>(L.nchunks) * 8);
+    auto dev_slot = [&](const HSlot& h, bool lo_plane) {
+        Slot sl{};
+        sl.dy = static_cast<int8_t>(h.kh - L.pad);
+        sl.dx = static_cast<int8_t>(h.kw - L.pad);
+        sl.seg = static_cast<uint8_t>(h.seg + (lo_plane ? kMaxSeg / 2 : 0));
+        sl.valid = 1;
+        sl.choff = static_cast<uint16_t>(h.choff);
+        return sl;
+    };
+    auto push_dev_slots = [&](const std::vector<HSlot>& ds) {
+        for (int j = 0; j < 8; ++j) {
+            const int d = exact ? (j & 3) : j;
+            if (d < static_cast<int>(ds.size())) slots.push_back(dev_slot(ds[d], exact && j >= 4));
+            else slots.push_back(Slot{});
+        }
+    };
+    if (!L.ric) {
+        std::vector<HSlot> all;
+        for (int kh = 0; kh < k; ++kh)
+            for (int kw = 0; kw < k; ++kw)
+                for (size_t si = 0; si < L.segs.size(); ++si) {
+                    const SegDef& s = L.segs[si];
+                    for (int c8 = 0; c8 < s.nch; c8 += 8)
+                        all.push_back(HSlot{kh, kw, (int)si, s.choff + c8, s.wch0 + c8, std::max(0, std::min(8, s.wn - c8))});
+                }
+        for (size_t i = 0; i < all.size(); i += dpc) {
+            std::vector<HSlot> ds(all.begin() + i, all.begin() + std::min(all.size(), i + dpc));
+            push_dev_slots(ds);
+            chunks.push_back(ds);
+        }
+        L.nblocks = 0;
+    } else {
+        std::vector<HSlot> groups;            // channel groups over the concat, tap filled in per chunk
+        for (size_t si = 0; si < L.segs.size(); ++si) {
+            const SegDef& s = L.segs[si];
+            for (int c8 = 0; c8 < s.nch; c8 += 8)
+                groups.push_back(HSlot{0, 0, (int)si, s.choff + c8, s.wch0 + c8, std::max(0, std::min(8, s.wn - c8))});
+        }
+        L.nblocks = static_cast<int>((groups.size() + dpc - 1) / dpc);
+        for (int b = 0; b < L.nblocks; ++b) {
+            std::vector<HSlot> blk(groups.begin() + b * dpc, groups.begin() + std::min<size_t>(groups.size(), (b + 1) * dpc));
+            push_dev_slots(blk);                               // one slot row per BLOCK
+            for (int tap = 0; tap < 9; ++tap) {
+                std::vector<HSlot> ds = blk;
+                for (HSlot& h : ds) { h.kh = tap / 3; h.kw = tap % 3; }
+                chunks.push_back(ds);
+            }
+        }
+    }
+    L.nchunks = static_cast<int>(chunks.size());
     std::vector<ChunkHdr> hdrs(L.nchunks);
     const size_t tile = static_cast<size_t>(C) * 128;
-    std::vector<uint8_t> pack(static_cast<size_t>(nlog) * tile * (exact ? 3 : 1), 0);
+    std::vector<uint8_t> pack(static_cast<size_t>(L.nchunks) * tile * (exact ? 2 : 1), 0);
     size_t off = 0;
-    for (int q = 0; q < nlog; ++q) {
-        const int nslot = std::min<int>(8, (int)hs.size() - q * 8);
-        const int ksteps = (nslot + 1) / 2;
-        for (int pl = 0; pl < per; ++pl) {
-            const int qq = q * per + pl;
-            for (int j = 0; j < 8; ++j) {
-                Slot& sl = slots[static_cast<size_t>(qq) * 8 + j];
-                sl = Slot{0, 0, 0, 0, 0, 0};
-                if (j < nslot) {
-                    const HSlot& h = hs[q * 8 + j];
-                    sl.dy = static_cast<int8_t>(L.ric ? h.kh * 3 + h.kw : h.kh - L.pad);
-                    sl.dx = static_cast<int8_t>(L.ric ? 0 : h.kw - L.pad);
-                    sl.seg = static_cast<uint8_t>(h.seg + pl * (kMaxSeg / 2));
-                    sl.valid = 1;
-                    sl.choff = static_cast<uint16_t>(h.choff);
+    auto put = [&](size_t tile_off, int row, int slot, int ci, __half val) {
+        const size_t b = tile_off + static_cast<size_t>(row) * 128 + ((static_cast<size_t>(slot) ^ (row & 7)) << 4) + ci * 2;
+        std::memcpy(&pack[b], &val, 2);
+    };
+    for (int q = 0; q < L.nchunks; ++q) {
+        const std::vector<HSlot>& ds = chunks[q];
+        const int nd = static_cast<int>(ds.size());
+        const int steps = (nd + 1) / 2;                        // K=16 steps covering the data slots
+        ChunkHdr& hd = hdrs[q];
+        hd.pad_ = 0;
+        hd.b_off = static_cast<uint32_t>(off);
+        if (!exact) { hd.kmask = static_cast<uint8_t>((1 << steps) - 1); hd.kmask2 = 0; }
+        else { hd.kmask = static_cast<uint8_t>(((1 << steps) - 1) | (((1 << steps) - 1) << 2)); hd.kmask2 = static_cast<uint8_t>((1 << steps) - 1); }
+        // B tile(s): row o = output channel, 128 B = 64 K elements, 16-byte slots XOR-swizzled by (row & 7)
+        for (int o = 0; o < C; ++o)
+            for (int d = 0; d < nd; ++d) {
+                const HSlot& h = ds[d];
+                for (int ci = 0; ci < h.nvalid; ++ci) {
+                    const float wv = Wt[((static_cast<size_t>(o) * cin_total + h.wch + ci) * k + h.kh) * k + h.kw];
+                    const __half wh = __float2half_rn(wv);
+                    put(off, o, d, ci, wh);
+                    if (exact) {
+                        put(off, o, d + 4, ci, wh);                                            // x a_lo
+                        put(off + tile, o, d, ci, __float2half_rn(wv - __half2float(wh)));     // W_lo x a_hi
+                    }
                 }
             }
-            hdrs[qq].ksteps = static_cast<uint8_t>(ksteps);
-            hdrs[qq].wide = (exact && pl == 0) ? 1 : 0;
-            hdrs[qq].pad_ = 0;
-            hdrs[qq].b_off = static_cast<uint32_t>(off);
-            // B tile(s): row o = output channel, 128 B = 64 K elements, 16-byte groups XOR-swizzled by (row & 7)
-            const int nrows_sets = hdrs[qq].wide ? 2 : 1;
-            for (int set = 0; set < nrows_sets; ++set)
-                for (int o = 0; o < C; ++o)
-                    for (int j = 0; j < nslot; ++j) {
-                        const HSlot& h = hs[q * 8 + j];
-                        for (int ci = 0; ci < h.nvalid; ++ci) {
-                            const float wv = Wt[((static_cast<size_t>(o) * cin_total + h.wch + ci) * k + h.kh) * k + h.kw];
-                            const __half wh = __float2half_rn(wv);
-                            const __half val = (set == 0) ? wh : __float2half_rn(wv - __half2float(wh));
-                            const size_t row = static_cast<size_t>(set) * C + o;
-                            const size_t b = off + row * 128 + ((static_cast<size_t>(j) ^ (row & 7)) << 4) + ci * 2;
-                            std::memcpy(&pack[b], &val, 2);
-                        }
-                    }
-            off += tile * nrows_sets;
-        }
+        off += tile * (exact ? 2 : 1);
     }
     pack.resize(off);
     int rc;
@@ -370,49 +406,66 @@ std::vector<float> default_offsets(int h, int w) {
     return off;
 }
 
-// torchvision deform_conv2d bilinear rule -> per (tap, pixel) 4 weights and
-// clamped corner offsets.  Table order: 8 non-centre taps in raster order.
+// torchvision deform_conv2d bilinear rule for the RIC field.  Every non-centre
+// tap k (rotation index 0..7) samples at pixel + (cos, sin)(theta + k*pi/4), i.e. inside the 3x3
+// neighbourhood.  With o = octant of theta, tap k falls in the 45-degree sector m = (o + k) & 7, whose
+// 2x2 corner set is fixed: rows {-1,0} if m in 2..5 else {0,+1}; cols {-1,0} if m >= 4 else {0,+1}.
+// The table stores o and, in m order, the fractions (ly, lx) = sample - first corner, derived from
+// the reference's own fp32 arithmetic (py = float(y-1+i) + offset; floor; subtract).  Corners outside
+// the image contribute 0 in the kernel, which reproduces torchvision's border rule exactly.
 int build_level(dsu_engine* E, Level& lv, int h, int w) {
-    if (lv.h == h && lv.w == w && lv.w4) return DSU_OK;
+    if (lv.h == h && lv.w == w && lv.lyx) return DSU_OK;
     std::vector<float> off;
     auto it = E->user_offsets.find({h, w});
     off = (it != E->user_offsets.end()) ? it->second : default_offsets(h, w);
     const size_t hw = static_cast<size_t>(h) * w;
-    std::vector<float4> w4(8 * hw);
-    std::vector<char4> o4(8 * hw);
-    for (int tap = 0; tap < 9; ++tap) {
-        if (tap == 4) continue;
-        const int t8 = tap < 4 ? tap : tap - 1;
-        const int i = tap / 3, j = tap % 3;
-        for (int y = 0; y < h; ++y)
-            for (int x = 0; x < w; ++x) {
+    std::vector<float2> lyx(8 * hw);
+    std::vector<uint8_t> oct(hw);
+    float worst = 0.0f;
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            float dyv[8], dxv[8];
+            for (int kq = 0; kq < 8; ++kq) {
+                const int tap = kq < 4 ? kq : kq + 1, i = tap / 3, j = tap % 3;
                 const float py = static_cast<float>(y - 1 + i) + off[(static_cast<size_t>(2 * tap) * h + y) * w + x];
                 const float px = static_cast<float>(x - 1 + j) + off[(static_cast<size_t>(2 * tap + 1) * h + y) * w + x];
-                const bool inside = !(py <= -1.0f || py >= static_cast<float>(h) || px <= -1.0f || px >= static_cast<float>(w));
-                const float fl_y = std::floor(py), fl_x = std::floor(px);
-                const int hl = static_cast<int>(fl_y), wl = static_cast<int>(fl_x), hh_i = hl + 1, wh_i = wl + 1;
-                const float lh = py - fl_y, lw = px - fl_x, hh = 1.0f - lh, hw_ = 1.0f - lw;
-                const bool ok_hl = hl >= 0 && hl <= h - 1, ok_hh = hh_i >= 0 && hh_i <= h - 1;
-                const bool ok_wl = wl >= 0 && wl <= w - 1, ok_wh = wh_i >= 0 && wh_i <= w - 1;
-                float4 wv;
-                wv.x = (inside && ok_hl && ok_wl) ? hh * hw_ : 0.0f;
-                wv.y = (inside && ok_hl && ok_wh) ? hh * lw : 0.0f;
-                wv.z = (inside && ok_hh && ok_wl) ? lh * hw_ : 0.0f;
-                wv.w = (inside && ok_hh && ok_wh) ? lh * lw : 0.0f;
-                auto cl = [](int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); };
-                char4 ov;
-                ov.x = static_cast<signed char>(cl(hl, h - 1) - y);
-                ov.y = static_cast<signed char>(cl(hh_i, h - 1) - y);
-                ov.z = static_cast<signed char>(cl(wl, w - 1) - x);
-                ov.w = static_cast<signed char>(cl(wh_i, w - 1) - x);
-                w4[t8 * hw + static_cast<size_t>(y) * w + x] = wv;
-                o4[t8 * hw + static_cast<size_t>(y) * w + x] = ov;
+                const float fy = std::floor(py), fx = std::floor(px);
+                dyv[kq] = (fy - static_cast<float>(y)) + (py - fy);     // integer part + the reference's lh
+                dxv[kq] = (fx - static_cast<float>(x)) + (px - fx);
             }
-    }
+            float th = std::atan2(dxv[0], dyv[0]);
+            if (th < 0) th += 2.0f * static_cast<float>(M_PI);
+            const int o0 = static_cast<int>(std::floor(th / (static_cast<float>(M_PI) / 4.0f))) & 7;
+            int best_o = o0;
+            float best_v = 1e9f;
+            for (int cand = 0; cand < 3; ++cand) {
+                const int o = (o0 + (cand == 0 ? 0 : (cand == 1 ? 7 : 1))) & 7;
+                float viol = 0.0f;
+                for (int kq = 0; kq < 8; ++kq) {
+                    const int m = (o + kq) & 7;
+                    const float ly = dyv[kq] - ((m >= 2 && m <= 5) ? -1.0f : 0.0f);
+                    const float lx = dxv[kq] - ((m >= 4) ? -1.0f : 0.0f);
+                    viol = std::max(viol, std::max(std::max(-ly, ly - 1.0f), std::max(-lx, lx - 1.0f)));
+                }
+                if (viol < best_v) { best_v = viol; best_o = o; }
+            }
+            worst = std::max(worst, best_v);
+            const size_t e = static_cast<size_t>(y) * w + x;
+            oct[e] = static_cast<uint8_t>(best_o);
+            for (int kq = 0; kq < 8; ++kq) {
+                const int m = (best_o + kq) & 7;
+                const float ly = dyv[kq] - ((m >= 2 && m <= 5) ? -1.0f : 0.0f);
+                const float lx = dxv[kq] - ((m >= 4) ? -1.0f : 0.0f);
+                lyx[e * 8 + m] = make_float2(std::min(1.0f, std::max(0.0f, ly)), std::min(1.0f, std::max(0.0f, lx)));
+            }
+        }
+    if (worst > 1e-3f)
+        return fail(DSU_E_INVALID, "RIC offsets are not unit-circle samples (generate_coordinates, models.py:551-604): a tap "
+                                   "misses its 45-degree sector by " + std::to_string(worst));
     int rc;
-    if ((rc = upload(&lv.w4, w4))) return rc;
-    if ((rc = upload(&lv.off, o4))) return rc;
-    lv.h = h; lv.w = w;
+    if ((rc = upload(&lv.lyx, lyx))) return rc;
+    if ((rc = upload(&lv.oct, oct))) return rc;
+    lv.h = h; lv.w = w; lv.max_clamp = worst;
     return DSU_OK;
 }
 
@@ -452,12 +505,19 @@ int ensure_shape(dsu_engine* E, int B, int H, int W) {
     return DSU_OK;
 }
 
-int pick_stages(int a_bytes, int b_bytes, bool pair) {
-    const int stage = a_bytes + b_bytes;
-    int s = (108 * 1024) / stage;          // two CTAs per SM when possible
+// stage counts: plain conv shares one ring depth for A and B and aims at two CTAs per SM;
+// RIC keeps one A buffer per tap (9) and gives the rest of the SM's shared memory to the weight ring.
+void pick_stages(bool ric, int b_bytes, int* sa, int* sb) {
+    if (ric) {
+        *sa = 9;
+        *sb = std::max(2, std::min(kMaxStagesB, (227 * 1024 - 9 * kABytes - 8 * 1024) / b_bytes));
+        return;
+    }
+    const int stage = kABytes + b_bytes;
+    int s = (108 * 1024) / stage;
     if (s < 2) s = (216 * 1024) / stage;
-    if (pair) s &= ~1;
-    return std::max(2, std::min(kMaxStages, s));
+    s = std::max(2, std::min(kMaxStagesB, s));
+    *sa = s; *sb = s;
 }
 
 int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgba, const uint8_t* alpha_src,
@@ -479,12 +539,11 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
         p.Hin = H >> src_level; p.Win = W >> src_level;
         p.up = L.up; p.Hv = p.Hin << L.up; p.Wv = p.Win << L.up;
         p.stride = L.stride; p.ric = L.ric; p.exact = E->exact ? 1 : 0;
-        p.nchunks = L.nchunks; p.Cout = L.cout;
-        p.a_bytes = kTileM * 128;
+        p.nchunks = L.nchunks; p.nblocks = L.nblocks; p.Cout = L.cout;
         p.b_bytes = (E->exact ? 2 : 1) * L.cout * 128;
-        p.nstages = pick_stages(p.a_bytes, p.b_bytes, E->exact && L.ric);
+        pick_stages(L.ric != 0, p.b_bytes, &p.sa, &p.sb);
         int cols = 32;
-        while (cols < (E->exact ? 2 : 1) * L.cout) cols *= 2;
+        while (cols < L.cout) cols *= 2;
         p.tmem_cols = cols;
         p.slots = L.d_slots; p.hdrs = L.d_hdrs; p.wpack = L.d_wpack;
         for (size_t i = 0; i < L.segs.size(); ++i) {
@@ -493,7 +552,7 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
             p.seg[i + kMaxSeg / 2].ptr = E->buf_lo[L.segs[i].buf];
             p.seg[i + kMaxSeg / 2].pitch = E->buf_C[L.segs[i].buf];
         }
-        if (L.ric) { p.ric_w = E->lv[L.level_out].w4; p.ric_off = E->lv[L.level_out].off; }
+        if (L.ric) { p.ric_lyx = E->lv[L.level_out].lyx; p.ric_oct = E->lv[L.level_out].oct; }
         EpiParams& e = p.epi;
         e.scale = L.d_scale; e.shift = L.d_shift; e.scale2 = L.d_scale2; e.shift2 = L.d_shift2;
         e.act = L.act; e.resid_in = L.resid_in; e.resid_out = L.resid_out; e.resid = E->resid;
@@ -572,7 +631,7 @@ void dsu_destroy(dsu_handle h) {
         cudaFree(L.d_scale); cudaFree(L.d_shift); cudaFree(L.d_scale2); cudaFree(L.d_shift2);
     }
     for (int b = 0; b < NBUF; ++b) { cudaFree(h->buf_hi[b]); cudaFree(h->buf_lo[b]); }
-    for (int l = 0; l < 3; ++l) { cudaFree(h->lv[l].w4); cudaFree(h->lv[l].off); }
+    for (int l = 0; l < 3; ++l) { cudaFree(h->lv[l].lyx); cudaFree(h->lv[l].oct); }
     cudaFree(h->resid); cudaFree(h->d_w12); cudaFree(h->d_b12);
     cudaFree(h->io_color); cudaFree(h->io_pos); cudaFree(h->io_edge); cudaFree(h->io_out);
     delete h;
@@ -694,7 +753,7 @@ size_t dsu_workspace_bytes(dsu_handle h, int32_t B, int32_t H, int32_t W) {
             total += static_cast<size_t>(B) * (H >> h->buf_level[b]) * (W >> h->buf_level[b]) * h->buf_C[b] * 2 * (h->exact ? 2 : 1);
     if (h->cfg.resnet_blocks > 0) total += static_cast<size_t>(B) * (H >> 2) * (W >> 2) * h->cfg.filters[2] * 4;
     if (h->cfg.kind == DSU_KIND_GENERATORJ_RIC)
-        for (int l = 0; l < 3; ++l) total += static_cast<size_t>(H >> l) * (W >> l) * 8 * 20;
+        for (int l = 0; l < 3; ++l) total += static_cast<size_t>(H >> l) * (W >> l) * 65;
     return total;
 }
 

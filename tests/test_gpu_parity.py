@@ -1,0 +1,328 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI via the Python mirror classes, against the
+CPU oracle and the golden vectors minted from the live reference.
+
+Tolerances: fp32 outputs within 1e-3 max-abs (BASELINE.json north_star) in the parity-grade fp16x3
+mode; the single-pass fp16 mode is checked against its documented error bound; uint8 steps are
+bit-exact on identical fp32 inputs.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import DEFAULT_ARGS, VARIANT_ARGS
+import drawingspinup_b200 as dsu
+from drawingspinup_b200 import capi, synth
+from oracle import reference_port as rp
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3            # north_star: max-abs fp32 vs the reference forward
+TOL_FP16 = 2.5e-2     # single-pass fp16 operands on the (deliberately sensitive) synthetic weights
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def _model(stage, dev, precision="fp16x3", args=None, seed=1234, **sd_kw):
+    a = dict(DEFAULT_ARGS if args is None else args)
+    cls = dsu.GeneratorJ_RIC if stage == 1 else dsu.GeneratorJ
+    sd = synth.to_torch_state_dict(synth.make_state_dict(
+        stage, seed=seed, filters=a["filters"], resnet_blocks=a["resnet_blocks"], input_channels=a["input_channels"],
+        tanh=a["tanh"], append_smoothers=a["append_smoothers"], use_bias=a["use_bias"], out_gain=0.25, **sd_kw))
+    m = cls(precision=precision, **a)
+    m.load_state_dict(sd)
+    return m.to(dev).eval(), sd
+
+
+def _oracle(stage, sd, x, args=None):
+    a = DEFAULT_ARGS if args is None else args
+    cfg = dict(rp.default_config(stage), **{k: a[k] for k in ("resnet_blocks", "tanh", "append_smoothers", "use_bias")})
+    with torch.no_grad():
+        if stage == 1:
+            return rp.generator_j_ric_forward(sd, x, cfg, use_torchvision=True)
+        return rp.generator_j_forward(sd, x, cfg)
+
+
+def _frames_tensor(b, h, w, seed, stage):
+    color, pos, edge = synth.make_frames(b, h, w, seed=seed)
+    x = np.stack([rp.frame_to_tensor(color[i], pos[i], edge[i] if stage == 2 else None)[0] for i in range(b)])
+    return torch.from_numpy(x)
+
+
+# ------------------------------------------------------------------ whole-network parity
+@pytest.mark.parametrize("stage", [1, 2])
+@pytest.mark.parametrize("shape", [(2, 64, 48), (1, 72, 100), (3, 32, 32)])
+def test_forward_matches_oracle_fp16x3(dev, stage, shape):
+    b, h, w = shape
+    m, sd = _model(stage, dev)
+    x = _frames_tensor(b, h, w, seed=h + w, stage=stage)
+    with torch.no_grad():
+        y = m(x.to(dev)).cpu()
+    assert y.shape == (b, 3, h, w) and y.dtype == torch.float32
+    assert (y - _oracle(stage, sd, x)).abs().max().item() < TOL
+
+
+@pytest.mark.parametrize("stage", [1, 2])
+def test_forward_matches_reference_golden(dev, golden_dir, stage):
+    g = np.load(os.path.join(golden_dir, "generator_stage%d.npz" % stage))
+    m, _ = _model(stage, dev, seed=int(g["seed"]))
+    with torch.no_grad():
+        y = m(torch.from_numpy(g["x"]).to(dev)).cpu().numpy()
+    assert np.abs(y - g["y"]).max() < TOL
+
+
+@pytest.mark.parametrize("stage", [1, 2])
+def test_variant_configuration_matches_reference_golden(dev, golden_dir, stage):
+    """use_bias=True, tanh=False, no smoothers, 2 blocks, other filters, 5 input channels."""
+    g = np.load(os.path.join(golden_dir, "generator_variant_stage%d.npz" % stage))
+    m, _ = _model(stage, dev, args=VARIANT_ARGS, seed=77)
+    with torch.no_grad():
+        y = m(torch.from_numpy(g["x"]).to(dev)).cpu().numpy()
+    scale = max(1.0, float(np.abs(g["y"]).max()))       # no tanh: outputs are unbounded, tolerance relative to range
+    assert np.abs(y - g["y"]).max() < TOL * scale
+
+
+@pytest.mark.parametrize("stage", [1, 2])
+def test_single_pass_fp16_error_bound(dev, stage):
+    m, sd = _model(stage, dev, precision="fp16")
+    x = _frames_tensor(2, 64, 64, seed=3, stage=stage)
+    with torch.no_grad():
+        y = m(x.to(dev)).cpu()
+    err = (y - _oracle(stage, sd, x)).abs()
+    assert err.max().item() < TOL_FP16 and err.mean().item() < 2e-3
+
+
+@pytest.mark.parametrize("stage", [1, 2])
+def test_nondefault_offsets_builtin_table(dev, stage):
+    """The engine's own generate_coordinates restatement (no torch offsets supplied) also meets parity."""
+    if stage == 2:
+        pytest.skip("stage 2 has no RIC field")
+    m, sd = _model(stage, dev)
+    m._prepare_shape = lambda h, w: None          # do not hand torch's offsets to the engine
+    x = _frames_tensor(1, 48, 64, seed=8, stage=stage)
+    with torch.no_grad():
+        y = m(x.to(dev)).cpu()
+    assert (y - _oracle(stage, sd, x)).abs().max().item() < TOL
+
+
+# ------------------------------------------------------------------ size-independent properties at full size
+@pytest.mark.parametrize("stage", [1, 2])
+def test_batch_invariance_and_determinism_512(dev, stage):
+    m, _ = _model(stage, dev, precision="fp16")
+    x = _frames_tensor(3, 512, 512, seed=21, stage=stage).to(dev)
+    with torch.no_grad():
+        full = m(x)
+        again = m(x)
+        one = m(x[1:2])
+    assert torch.equal(full, again)                      # deterministic
+    assert torch.equal(full[1:2], one)                   # KAT (vi): a frame does not depend on its batch
+    assert torch.isfinite(full).all() and full.abs().max().item() <= 1.0
+
+
+def test_frame_size_528_partial_tiles(dev):
+    """KAT (vii): jumping's real frame size (blender_animation.py:70-77): 528/264/132 are not tile multiples."""
+    m16, _ = _model(2, dev, precision="fp16")
+    mx, sd = _model(2, dev, precision="fp16x3")
+    x = _frames_tensor(1, 528, 528, seed=5, stage=2)
+    with torch.no_grad():
+        y = mx(x.to(dev)).cpu()
+        y16 = m16(x.to(dev)).cpu()
+    ref = _oracle(2, sd, x)
+    assert (y - ref).abs().max().item() < TOL
+    assert (y16 - ref).abs().max().item() < TOL_FP16
+
+
+def test_stage1_dead_smoother_weights_do_not_matter(dev):
+    """KAT (iii), models.py:348-352: conv_11_a.0 / .2 are loaded (strict keys) but never influence stage 1."""
+    m, sd = _model(1, dev)
+    x = _frames_tensor(1, 48, 48, seed=2, stage=1).to(dev)
+    with torch.no_grad():
+        a = m(x)
+        sd2 = dict(sd)
+        sd2["conv_11_a.0.weight"] = torch.randn_like(sd["conv_11_a.0.weight"])
+        sd2["conv_11_a.2.running_var"] = torch.rand_like(sd["conv_11_a.2.running_var"]) + 0.5
+        m.load_state_dict(sd2)
+        b = m(x)
+    assert torch.equal(a, b)
+
+
+def test_weight_reload_changes_output(dev):
+    m, sd = _model(2, dev)
+    x = _frames_tensor(1, 32, 32, seed=2, stage=2).to(dev)
+    with torch.no_grad():
+        a = m(x)
+        sd2 = synth.to_torch_state_dict(synth.make_state_dict(2, seed=99, out_gain=0.25))
+        m.load_state_dict(sd2)
+        b = m(x).cpu()
+    assert not torch.equal(a.cpu(), b)
+    assert (b - _oracle(2, sd2, x.cpu())).abs().max().item() < TOL
+
+
+def test_input_validation(dev):
+    m, _ = _model(2, dev)
+    with torch.no_grad():
+        with pytest.raises(RuntimeError):
+            m(torch.zeros(1, 5, 32, 32, device=dev))          # wrong channel count
+        with pytest.raises(RuntimeError, match="multiples of 4"):
+            m(torch.zeros(1, 6, 30, 32, device=dev))          # int(H/2), int(H/4) levels need H % 4 == 0
+    m.train()
+    with pytest.raises(RuntimeError, match="inference-only"):
+        m(torch.zeros(1, 6, 32, 32, device=dev))
+
+
+# ------------------------------------------------------------------ uint8 / frame steps: bit exact
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def test_to_image_space_bit_exact(dev, golden_dir):
+    g = np.load(os.path.join(golden_dir, "to_image_space.npz"))
+    rng = np.random.default_rng(0)
+    x = np.concatenate([g["kat_in"], g["rnd_in"], rng.uniform(-1.5, 1.5, 1 << 16).astype(np.float32),
+                        (np.arange(-300, 300, dtype=np.float32) / 255.0)])
+    xd = torch.from_numpy(x).to(dev)
+    out = torch.empty(x.size, dtype=torch.uint8, device=dev)
+    capi.check(capi.lib().dsu_to_image_space(_ptr(xd), _ptr(out), x.size, None), "to_image_space")
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), rp.to_image_space(x))
+    assert list(out.cpu().numpy()[:9]) == [0, 0, 63, 127, 127, 191, 254, 255, 255]
+
+
+def test_frames_to_tensor_bit_exact(dev, golden_dir):
+    g = np.load(os.path.join(golden_dir, "dataset_transform.npz"))
+    color, pos, edge = (torch.from_numpy(g[k]).to(dev) for k in ("color", "pos", "edge"))
+    b, h, w, _ = color.shape
+    for e, key in ((None, "pre_stage1"), (edge, "pre_stage2")):
+        pre = torch.empty((b, 6, h, w), dtype=torch.float32, device=dev)
+        mask = torch.empty((b, 1, h, w), dtype=torch.float32, device=dev)
+        capi.check(capi.lib().dsu_frames_to_tensor(_ptr(color), _ptr(pos), _ptr(e) if e is not None else None,
+                                                   b, h, w, _ptr(pre), _ptr(mask), None), "frames_to_tensor")
+        torch.cuda.synchronize()
+        assert np.array_equal(pre.cpu().numpy(), g[key])          # reference DatasetFullImages output
+        assert np.array_equal(mask.cpu().numpy(), g["pre_mask"])
+
+
+def test_overlap_edge_and_compose_bit_exact(dev):
+    color, pos, edge = synth.make_frames(2, 40, 56, seed=4)
+    rgba = torch.from_numpy(color).to(dev).clone()
+    capi.check(capi.lib().dsu_overlap_edge(_ptr(torch.from_numpy(edge).to(dev)), _ptr(rgba), 2 * 40 * 56, None), "overlap")
+    want = np.stack([rp.overlap_edge_on_img(edge[i], color[i]) for i in range(2)])
+    assert np.array_equal(rgba.cpu().numpy(), want)
+    rng = np.random.default_rng(1)
+    y = rng.uniform(-1.3, 1.3, (2, 3, 40, 56)).astype(np.float32)
+    mask = np.stack([rp.frame_to_tensor(color[i], pos[i])[1] for i in range(2)])
+    out = torch.empty((2, 40, 56, 4), dtype=torch.uint8, device=dev)
+    capi.check(capi.lib().dsu_compose_rgba(_ptr(torch.from_numpy(y).to(dev)), _ptr(torch.from_numpy(mask).to(dev)),
+                                           2, 40, 56, _ptr(out), None), "compose")
+    want = np.stack([rp.compose_rgba(y[i], mask[i]) for i in range(2)])
+    assert np.array_equal(out.cpu().numpy(), want)
+
+
+def test_pos2edge_bit_exact(dev, golden_dir):
+    g = np.load(os.path.join(golden_dir, "pos2edge.npz"))
+    pos = torch.from_numpy(g["pos"]).to(dev)
+    b, h, w, _ = pos.shape
+    out = torch.empty((b, h, w), dtype=torch.uint8, device=dev)
+    capi.check(capi.lib().dsu_pos2edge(_ptr(pos), b, h, w, _ptr(out), None), "pos2edge")
+    assert np.array_equal(out.cpu().numpy(), g["edges"])          # the reference's own cv2 result
+    _, pos2, _ = synth.make_frames(2, 96, 80, seed=12)
+    out2 = torch.empty((2, 96, 80), dtype=torch.uint8, device=dev)
+    capi.check(capi.lib().dsu_pos2edge(_ptr(torch.from_numpy(pos2).to(dev)), 2, 96, 80, _ptr(out2), None), "pos2edge")
+    assert np.array_equal(out2.cpu().numpy(), np.stack([rp.pos2edge(pos2[i]) for i in range(2)]))
+
+
+# ------------------------------------------------------------------ fused frame path and the two-stage chain
+def test_fused_frame_path_equals_unfused_steps(dev):
+    """forward_frames == frames_to_tensor -> forward -> compose (bitwise: same kernels, same fp32 values)."""
+    b, h, w = 2, 64, 48
+    color, pos, edge = synth.make_frames(b, h, w, seed=6)
+    for stage in (1, 2):
+        m, sd = _model(stage, dev)
+        c, p = torch.from_numpy(color).to(dev), torch.from_numpy(pos).to(dev)
+        e = torch.from_numpy(edge).to(dev) if stage == 2 else None
+        with torch.no_grad():
+            out, y = m.forward_frames(c, p, e, return_float=True)
+            x = torch.from_numpy(np.stack([rp.frame_to_tensor(color[i], pos[i], edge[i] if stage == 2 else None)[0]
+                                           for i in range(b)])).to(dev)
+            y2 = m(x)
+        assert torch.equal(y, y2)
+        want = np.stack([rp.compose_rgba(y[i].cpu().numpy(), rp.frame_to_tensor(color[i], pos[i])[1]) for i in range(b)])
+        assert np.array_equal(out.cpu().numpy(), want)
+
+
+def test_two_stage_chain_against_oracle_chain(dev):
+    """stage 1 -> uint8 -> edge burn-in -> stage 2 (test_stage1.py + test_stage2.py back to back)."""
+    from drawingspinup_b200.pipeline import StylizationPipeline
+    b, h, w = 2, 64, 64
+    color, pos, edge = synth.make_frames(b, h, w, seed=13)
+    sd1 = synth.to_torch_state_dict(synth.make_state_dict(1, out_gain=0.25))
+    sd2 = synth.to_torch_state_dict(synth.make_state_dict(2, out_gain=0.25))
+    pipe = StylizationPipeline(sd1, sd2, dev, precision="fp16x3", batch=2)
+    out2, out1 = pipe.run(torch.from_numpy(color).to(dev), torch.from_numpy(pos).to(dev),
+                          torch.from_numpy(edge).to(dev), keep_stage1=True)
+    out1, out2 = out1.cpu().numpy(), out2.cpu().numpy()
+    with torch.no_grad():
+        x1 = torch.from_numpy(np.stack([rp.frame_to_tensor(color[i], pos[i])[0] for i in range(b)]))
+        y1 = rp.generator_j_ric_forward(sd1, x1, use_torchvision=True)
+    want1 = np.stack([rp.compose_rgba(y1[i].numpy(), rp.frame_to_tensor(color[i], pos[i])[1]) for i in range(b)])
+    d1 = np.abs(out1.astype(np.int32) - want1.astype(np.int32))
+    assert d1.max() <= 1 and (d1 > 0).mean() < 0.01          # <=1 LSB where fp32 sits on an integer boundary
+    assert np.array_equal(out1[..., 3], color[..., 3])        # alpha round trip is exact
+    # stage 2 on the engine's own stage-1 bytes (what test_stage2.py would read back from disk)
+    with torch.no_grad():
+        x2 = torch.from_numpy(np.stack([rp.frame_to_tensor(out1[i], pos[i], edge[i])[0] for i in range(b)]))
+        y2 = rp.generator_j_forward(sd2, x2)
+    want2 = np.stack([rp.compose_rgba(y2[i].numpy(), rp.frame_to_tensor(out1[i], pos[i])[1]) for i in range(b)])
+    d2 = np.abs(out2.astype(np.int32) - want2.astype(np.int32))
+    assert d2.max() <= 1 and (d2 > 0).mean() < 0.01
+    # host-buffer entry point gives the same bytes
+    host_out = torch.empty((b, h, w, 4), dtype=torch.uint8).pin_memory()
+    pipe.run_host(torch.from_numpy(color).pin_memory(), torch.from_numpy(pos).pin_memory(),
+                  torch.from_numpy(edge).pin_memory(), host_out)
+    assert np.array_equal(host_out.numpy(), out2)
+
+
+def test_c_abi_host_entry_point(dev):
+    b, h, w = 1, 32, 48
+    color, pos, edge = synth.make_frames(b, h, w, seed=17)
+    m, _ = _model(2, dev)
+    c, p, e = (torch.from_numpy(a).pin_memory() for a in (color, pos, edge))
+    out = torch.empty((b, h, w, 4), dtype=torch.uint8).pin_memory()
+    m.forward_frames_host(c, p, e, out, dev)
+    with torch.no_grad():
+        want = m.forward_frames(c.to(dev), p.to(dev), e.to(dev)).cpu()
+    assert torch.equal(out, want)
+
+
+def test_flop_model_and_launch_count(dev):
+    m1, _ = _model(1, dev)
+    m2, _ = _model(2, dev)
+    assert abs(m1.algorithmic_flops(1, 512, 512) - 297.56e9) / 297.56e9 < 1e-3
+    assert abs(m2.algorithmic_flops(1, 512, 512) - 543.72e9) / 543.72e9 < 1e-3
+    # ingest + fused convs (+ 2 max-pools in stage 1; its dead smoother conv is not launched)
+    assert m1.kernel_launches(1, 512, 512) == 1 + 21 + 2 and m2.kernel_launches(1, 512, 512) == 1 + 22
+
+
+def test_multi_gpu_shard_equivalence(dev):
+    """N-GPU frame sharding == single GPU, bitwise."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from drawingspinup_b200.pipeline import StylizationPipeline, shard_range
+    color, pos, edge = synth.make_frames(6, 64, 64, seed=31)
+    sd1 = synth.to_torch_state_dict(synth.make_state_dict(1, out_gain=0.25))
+    sd2 = synth.to_torch_state_dict(synth.make_state_dict(2, out_gain=0.25))
+    outs = []
+    single = None
+    for r in range(2):
+        d = torch.device("cuda", r)
+        pipe = StylizationPipeline(sd1, sd2, d, precision="fp16", batch=4)
+        lo, hi = shard_range(6, r, 2)
+        outs.append(pipe.run(*(torch.from_numpy(a[lo:hi]).to(d) for a in (color, pos, edge))).cpu())
+        if r == 0:
+            single = pipe.run(*(torch.from_numpy(a).to(d) for a in (color, pos, edge))).cpu()
+    assert torch.equal(torch.cat(outs), single)
