@@ -210,15 +210,16 @@ def test_frames_to_tensor_bit_exact(dev, golden_dir):
 def test_overlap_edge_and_compose_bit_exact(dev):
     color, pos, edge = synth.make_frames(2, 40, 56, seed=4)
     rgba = torch.from_numpy(color).to(dev).clone()
-    capi.check(capi.lib().dsu_overlap_edge(_ptr(torch.from_numpy(edge).to(dev)), _ptr(rgba), 2 * 40 * 56, None), "overlap")
+    edge_d = torch.from_numpy(edge).to(dev)              # keep device tensors alive across the async launches
+    capi.check(capi.lib().dsu_overlap_edge(_ptr(edge_d), _ptr(rgba), 2 * 40 * 56, None), "overlap")
     want = np.stack([rp.overlap_edge_on_img(edge[i], color[i]) for i in range(2)])
     assert np.array_equal(rgba.cpu().numpy(), want)
     rng = np.random.default_rng(1)
     y = rng.uniform(-1.3, 1.3, (2, 3, 40, 56)).astype(np.float32)
     mask = np.stack([rp.frame_to_tensor(color[i], pos[i])[1] for i in range(2)])
     out = torch.empty((2, 40, 56, 4), dtype=torch.uint8, device=dev)
-    capi.check(capi.lib().dsu_compose_rgba(_ptr(torch.from_numpy(y).to(dev)), _ptr(torch.from_numpy(mask).to(dev)),
-                                           2, 40, 56, _ptr(out), None), "compose")
+    y_d, mask_d = torch.from_numpy(y).to(dev), torch.from_numpy(mask).to(dev)
+    capi.check(capi.lib().dsu_compose_rgba(_ptr(y_d), _ptr(mask_d), 2, 40, 56, _ptr(out), None), "compose")
     want = np.stack([rp.compose_rgba(y[i], mask[i]) for i in range(2)])
     assert np.array_equal(out.cpu().numpy(), want)
 
@@ -232,7 +233,8 @@ def test_pos2edge_bit_exact(dev, golden_dir):
     assert np.array_equal(out.cpu().numpy(), g["edges"])          # the reference's own cv2 result
     _, pos2, _ = synth.make_frames(2, 96, 80, seed=12)
     out2 = torch.empty((2, 96, 80), dtype=torch.uint8, device=dev)
-    capi.check(capi.lib().dsu_pos2edge(_ptr(torch.from_numpy(pos2).to(dev)), 2, 96, 80, _ptr(out2), None), "pos2edge")
+    pos2_d = torch.from_numpy(pos2).to(dev)
+    capi.check(capi.lib().dsu_pos2edge(_ptr(pos2_d), 2, 96, 80, _ptr(out2), None), "pos2edge")
     assert np.array_equal(out2.cpu().numpy(), np.stack([rp.pos2edge(pos2[i]) for i in range(2)]))
 
 
