@@ -12,10 +12,18 @@ constexpr int kTileM = 128;     // = UMMA M
 constexpr int kChunkK = 64;     // fp16 K elements per smem row (128 B, SWIZZLE_128B)
 constexpr int kABytes = kTileM * 128;   // bytes of one A stage
 constexpr int kWorkers = 256;   // producer / epilogue threads (warps 0-7)
-constexpr int kThreads = 320;   // + warp 8 (MMA issue, TMEM alloc) + warp 9 (weight loader)
+// A single warp sustains only ~100 cycles per tcgen05.mma in SS mode (tools/umma_rate.cu), far above the
+// 32/64-cycle execution time of an M=128, N=64/128, K=16 MMA, so a CTA runs several issuing warps, each
+// with its own TMEM accumulator (sub-tile and/or K split; partial sums are added in the epilogue).
+constexpr int kIssuersTap = 1;   // tap-mode plain conv
+constexpr int kIssuersRic = 3;   // RIC: taps t with t % 3 == issuer
+constexpr int kIssuersHalo = 4;  // halo: ns sub-tiles x ks K-splits <= 4
+constexpr int kThreadsTap = (8 + kIssuersTap + 1) * 32;
+constexpr int kThreadsRic = (8 + kIssuersRic + 1) * 32;
+constexpr int kThreadsHalo = (8 + kIssuersHalo + 1) * 32;
 constexpr int kMaxSeg = 6;      // concat segments (second half = lo planes in exact mode)
 constexpr int kMaxStagesA = 9;  // RIC keeps one A buffer per tap resident
-constexpr int kMaxStagesB = 4;
+constexpr int kMaxStagesB = 16;
 
 // One 16-byte (8-channel) K slot: which tap of which source segment fills it.
 // plain conv: one entry per (chunk, slot).  RIC conv: one entry per (64-channel block, slot) - the
@@ -74,7 +82,14 @@ struct ConvParams {
     int Hv, Wv;             // virtual conv-input geometry = (Hin << up, Win << up)
     int stride, up, ric, exact;
     int nchunks, nblocks, Cout, sa, sb, tmem_cols;
-    int b_bytes;            // bytes per B stage
+    int b_bytes;            // bytes per B stage = bytes of one chunk's weight tile(s) in wpack
+    // K-step masks (ChunkHdr semantics) as launch constants so the issuing warp stays uniform:
+    // every chunk uses *_full except the ragged tail (tap mode: the last chunk; block modes: all
+    // chunks of the last channel block), which uses *_last
+    uint32_t kmask_full, kmask_last, kmask2_full, kmask2_last;
+    // halo mode (plain stride-1 convs): one (16+2p) x (8*ns+2p) pixel halo tile per 64-channel block
+    // is staged once and every tap reads a shifted window of it through the UMMA descriptor
+    int halo, ns, ks, ksize, pad, halo_w, halo_rows, halo_bytes;   // ks: K-split issuers per sub-tile
     const Slot* slots;      // plain: [nchunks][8]; RIC: [nblocks][8]
     const ChunkHdr* hdrs;   // [nchunks]
     const uint8_t* wpack;   // pre-swizzled B tiles
@@ -87,6 +102,8 @@ struct ConvParams {
 };
 
 cudaError_t launch_conv(const ConvParams& p, cudaStream_t stream);
+cudaError_t launch_conv_halo(const ConvParams& p, cudaStream_t stream);
+size_t conv_halo_smem_bytes(const ConvParams& p);
 size_t conv_smem_bytes(const ConvParams& p);
 
 }  // namespace dsu

@@ -1,0 +1,159 @@
+// Device helpers shared by the convolution kernels: fp16 pack/split, the exact uint8 conversion and
+// the fused epilogue (TMEM accumulator row -> BN/activation/residual -> fp16 NHWC / fp32 / uint8).
+#pragma once
+#include "conv.cuh"
+#include "ptx.cuh"
+
+namespace dsu {
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t v) {
+    return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
+__device__ __forceinline__ void unpack8(const uint4& raw, float* f) {
+    float2 a = unpack_h2(raw.x), b = unpack_h2(raw.y), c = unpack_h2(raw.z), d = unpack_h2(raw.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+// 8 fp32 -> packed fp16 hi and residual lo = fp16(v - hi)
+__device__ __forceinline__ void split8(const float* f, uint4& hi, uint4& lo) {
+    hi.x = pack_h2(f[0], f[1]); hi.y = pack_h2(f[2], f[3]); hi.z = pack_h2(f[4], f[5]); hi.w = pack_h2(f[6], f[7]);
+    float r[8];
+    unpack8(hi, r);
+    lo.x = pack_h2(f[0] - r[0], f[1] - r[1]); lo.y = pack_h2(f[2] - r[2], f[3] - r[3]);
+    lo.z = pack_h2(f[4] - r[4], f[5] - r[5]); lo.w = pack_h2(f[6] - r[6], f[7] - r[7]);
+}
+
+// exact fp32 -> uint8 of custom_transforms.py:7-8: ((clip(x,-1,1)+1)/2*255) truncated, fp32 ops in order
+__device__ __forceinline__ uint8_t to_u8(float x) {
+    x = fminf(fmaxf(x, -1.0f), 1.0f);
+    float t = __fmul_rn(__fmul_rn(__fadd_rn(x, 1.0f), 0.5f), 255.0f);
+    return static_cast<uint8_t>(static_cast<int>(t));
+}
+
+// epilogue parameters in shared memory: [scale C][shift C][scale2 C][shift2 C][w12 3C][b12 4]
+__device__ __forceinline__ void load_epilogue_params(const ConvParams& p, float* s_par, int tid, int nthreads) {
+    const int C = p.Cout;
+    for (int i = tid; i < C; i += nthreads) {
+        s_par[i] = p.epi.scale[i];
+        s_par[C + i] = p.epi.shift[i];
+        s_par[2 * C + i] = p.epi.scale2 ? p.epi.scale2[i] : 1.0f;
+        s_par[3 * C + i] = p.epi.shift2 ? p.epi.shift2[i] : 0.0f;
+        if (p.epi.w12) {
+            s_par[4 * C + i] = p.epi.w12[i];
+            s_par[5 * C + i] = p.epi.w12[C + i];
+            s_par[6 * C + i] = p.epi.w12[2 * C + i];
+        }
+    }
+    if (p.epi.w12 && tid < 3) s_par[7 * C + tid] = p.epi.b12[tid];
+}
+
+// One accumulator row (= one output pixel, all Cout columns) per thread.  `t_addr` = TMEM address of
+// this warp's lane quadrant at the accumulator's first column.  The two warps that share a lane
+// quadrant (chalf 0/1) split the 32-column batches; the conv_12 tail needs a whole row in one
+// thread, so only chalf 0 runs it.  Must be called by all 32 lanes of the warp (tcgen05.ld is
+// warp-collective); chalf is warp-uniform.
+// `nsplit` partial accumulators `split_stride` columns apart (K-split issuers) are summed first.
+__device__ __forceinline__ void epilogue_row(const ConvParams& p, const float* s_par, uint32_t t_addr,
+                                             int n, int oy, int ox, int chalf, int nsplit = 1, int split_stride = 0) {
+    const EpiParams& e = p.epi;
+    const int C = p.Cout;
+    const bool pix_ok = oy < p.Hout && ox < p.Wout;
+    const size_t opix = (static_cast<size_t>(n) * p.Hout + oy) * p.Wout + ox;
+    const int ncb = C / 32;
+    const bool tail = e.w12 != nullptr;
+    const int cb_first = tail ? 0 : chalf, cb_step = tail ? 1 : 2;
+    const bool active = tail ? (chalf == 0) : (chalf < ncb);
+    if (!active) return;
+    float y3[3] = {0.0f, 0.0f, 0.0f};
+    for (int cbi = cb_first; cbi < ncb; cbi += cb_step) {
+        const int cb = cbi * 32;
+        uint32_t v[32];
+        tmem_ld32(t_addr + cb, v);
+        tmem_ld_wait();
+        for (int sp = 1; sp < nsplit; ++sp) {
+            uint32_t u[32];
+            tmem_ld32(t_addr + sp * split_stride + cb, u);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(u[c]));
+        }
+        if (!pix_ok) continue;
+        float f[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            float x = fmaf(__uint_as_float(v[c]), s_par[cb + c], s_par[C + cb + c]);
+            if (e.act == 1) x = fmaxf(x, 0.0f);
+            else if (e.act == 2) x = x > 0.0f ? x : 0.2f * x;
+            if (e.scale2) x = fmaf(x, s_par[2 * C + cb + c], s_par[3 * C + cb + c]);
+            f[c] = x;
+        }
+        if (e.resid_in) {
+            const float4* rp = reinterpret_cast<const float4*>(e.resid + opix * C + cb);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 rv = rp[c];
+                f[4 * c] += rv.x; f[4 * c + 1] += rv.y; f[4 * c + 2] += rv.z; f[4 * c + 3] += rv.w;
+            }
+        }
+        if (e.resid_out) {
+            float4* rp = reinterpret_cast<float4*>(e.resid + opix * C + cb);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) rp[c] = make_float4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]);
+        }
+        if (e.out2_hi) {
+            uint4* o = reinterpret_cast<uint4*>(e.out2_hi + opix * e.out2_pitch + e.out2_choff + cb);
+            uint4* ol = e.out2_lo ? reinterpret_cast<uint4*>(e.out2_lo + opix * e.out2_pitch + e.out2_choff + cb) : nullptr;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint4 hi, lo;
+                split8(f + 8 * c, hi, lo);
+                o[c] = hi;
+                if (ol) ol[c] = lo;
+            }
+        }
+        if (e.out_relu) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) f[c] = fmaxf(f[c], 0.0f);
+        }
+        if (e.out_hi) {
+            uint4* o = reinterpret_cast<uint4*>(e.out_hi + opix * e.out_pitch + e.out_choff + cb);
+            uint4* ol = e.out_lo ? reinterpret_cast<uint4*>(e.out_lo + opix * e.out_pitch + e.out_choff + cb) : nullptr;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint4 hi, lo;
+                split8(f + 8 * c, hi, lo);
+                o[c] = hi;
+                if (ol) ol[c] = lo;
+            }
+        }
+        if (tail) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                y3[0] = fmaf(f[c], s_par[4 * C + cb + c], y3[0]);
+                y3[1] = fmaf(f[c], s_par[5 * C + cb + c], y3[1]);
+                y3[2] = fmaf(f[c], s_par[6 * C + cb + c], y3[2]);
+            }
+        }
+    }
+    if (tail && pix_ok) {
+        const size_t plane = static_cast<size_t>(p.Hout) * p.Wout;
+        const size_t pin = static_cast<size_t>(oy) * p.Wout + ox;
+        uint8_t rgb[3];
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+            float yv = y3[o] + s_par[7 * C + o];
+            if (e.tanh_flag) yv = tanhf(yv);
+            if (e.y_nchw) e.y_nchw[(static_cast<size_t>(n) * 3 + o) * plane + pin] = yv;
+            rgb[o] = to_u8(yv);
+        }
+        if (e.y_rgba) {
+            const uint8_t a = e.alpha_src ? e.alpha_src[opix * e.alpha_stride] : 255;
+            reinterpret_cast<uchar4*>(e.y_rgba)[opix] = make_uchar4(rgb[0], rgb[1], rgb[2], a);
+        }
+    }
+}
+
+}  // namespace dsu

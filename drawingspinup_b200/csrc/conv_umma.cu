@@ -20,8 +20,7 @@
 // "Exact" mode (split fp16): a K chunk holds 32 channels as [a_hi | a_lo]; it is multiplied by
 // [W_hi | W_hi] (4 K-steps) and its hi half again by W_lo (2 K-steps) into the same accumulator:
 // a_hi*W_hi + a_lo*W_hi + a_hi*W_lo, fp32-grade products at 3x the tensor work.
-#include "conv.cuh"
-#include "ptx.cuh"
+#include "conv_device.cuh"
 
 namespace dsu {
 
@@ -45,33 +44,6 @@ __host__ __device__ inline SmemLayout smem_layout(int sa, int sb, int b_bytes, i
     return L;
 }
 
-__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-}
-__device__ __forceinline__ float2 unpack_h2(uint32_t v) {
-    return __half22float2(*reinterpret_cast<const __half2*>(&v));
-}
-__device__ __forceinline__ void unpack8(const uint4& raw, float* f) {
-    float2 a = unpack_h2(raw.x), b = unpack_h2(raw.y), c = unpack_h2(raw.z), d = unpack_h2(raw.w);
-    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
-}
-// 8 fp32 -> packed fp16 hi and residual lo = fp16(v - hi)
-__device__ __forceinline__ void split8(const float* f, uint4& hi, uint4& lo) {
-    hi.x = pack_h2(f[0], f[1]); hi.y = pack_h2(f[2], f[3]); hi.z = pack_h2(f[4], f[5]); hi.w = pack_h2(f[6], f[7]);
-    float r[8];
-    unpack8(hi, r);
-    lo.x = pack_h2(f[0] - r[0], f[1] - r[1]); lo.y = pack_h2(f[2] - r[2], f[3] - r[3]);
-    lo.z = pack_h2(f[4] - r[4], f[5] - r[5]); lo.w = pack_h2(f[6] - r[6], f[7] - r[7]);
-}
-
-// exact fp32 -> uint8 of custom_transforms.py:7-8: ((clip(x,-1,1)+1)/2*255) truncated, fp32 ops in order
-__device__ __forceinline__ uint8_t to_u8(float x) {
-    x = fminf(fmaxf(x, -1.0f), 1.0f);
-    float t = __fmul_rn(__fmul_rn(__fadd_rn(x, 1.0f), 0.5f), 255.0f);
-    return static_cast<uint8_t>(static_cast<int>(t));
-}
-
 // Static corner set of rotated tap m (sample angle in [m*45, m*45+45) degrees):
 // row offset cos<0 for m in 2..5, column offset sin<0 for m in 4..7.
 __device__ __forceinline__ constexpr int quad_r0(int m) { return (m >= 2 && m <= 5) ? 0 : 1; }
@@ -80,7 +52,7 @@ __device__ __forceinline__ constexpr int quad_c0(int m) { return (m >= 4) ? 0 : 
 }  // namespace
 
 template <bool kRic>
-__global__ void __launch_bounds__(kThreads, kRic ? 1 : 2)
+__global__ void __launch_bounds__(kRic ? kThreadsRic : kThreadsTap, kRic ? 1 : 2)
 conv_umma_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_u32 = smem_u32(smem_raw);
@@ -88,7 +60,6 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
     uint8_t* smem = smem_raw + (base - raw_u32);
     const SmemLayout L = smem_layout(p.sa, p.sb, p.b_bytes, p.Cout, p.nchunks);
     float* s_par = reinterpret_cast<float*>(smem + L.par);
-    ChunkHdr* s_hdr = reinterpret_cast<ChunkHdr*>(smem + L.hdr);
     const uint32_t bar_full_a = base + L.bars;
     const uint32_t bar_empty_a = bar_full_a + kMaxStagesA * 8;
     const uint32_t bar_full_b = bar_empty_a + kMaxStagesA * 8;
@@ -116,27 +87,14 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                 mbar_init(bar_full_b + 8 * s, 1);
                 mbar_init(bar_empty_b + 8 * s, 1);
             }
-            mbar_init(bar_accum, 1);
+            mbar_init(bar_accum, kRic ? p.ks : 1);
             fence_mbar_init();
         }
         __syncwarp();
         tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
         tmem_relinquish();
     } else if (warp < 8) {
-        // epilogue parameters -> smem: [scale C][shift C][scale2 C][shift2 C][w12 3C][b12 4]
-        for (int i = tid; i < C; i += kWorkers) {
-            s_par[i] = p.epi.scale[i];
-            s_par[C + i] = p.epi.shift[i];
-            s_par[2 * C + i] = p.epi.scale2 ? p.epi.scale2[i] : 1.0f;
-            s_par[3 * C + i] = p.epi.shift2 ? p.epi.shift2[i] : 0.0f;
-            if (p.epi.w12) {
-                s_par[4 * C + i] = p.epi.w12[i];
-                s_par[5 * C + i] = p.epi.w12[C + i];
-                s_par[6 * C + i] = p.epi.w12[2 * C + i];
-            }
-        }
-        if (p.epi.w12 && tid < 3) s_par[7 * C + tid] = p.epi.b12[tid];
-        for (int i = tid; i < p.nchunks; i += kWorkers) s_hdr[i] = p.hdrs[i];
+        load_epilogue_params(p, s_par, tid, kWorkers);
     }
     tc_fence_before();
     __syncthreads();
@@ -308,147 +266,93 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         // ======================================================== epilogue (warps 0-7)
         mbar_wait(bar_accum, 0);
         tc_fence_after();
-        const EpiParams& e = p.epi;
-        const int quad = warp & 3, chalf = warp >> 2;
-        const int r = quad * 32 + lane;          // accumulator row = TMEM lane = patch pixel
-        const int oy = ty0 + (r >> 4);
-        const int oxe = tx0 + (r & 15);
-        const bool pix_ok = oy < p.Hout && oxe < p.Wout;
-        const size_t opix = (static_cast<size_t>(n) * p.Hout + oy) * p.Wout + oxe;
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-        const int ncb = C / 32;
-        // column batches are split between the two warps of a lane quadrant; the 1x1 tail needs a
-        // whole row in one thread, so only the first warp of each quadrant runs it
-        const bool tail = e.w12 != nullptr;
-        const int cb_first = tail ? 0 : chalf, cb_step = tail ? 1 : 2;
-        const bool active = tail ? (chalf == 0) : (chalf < ncb);
-        float y3[3] = {0.0f, 0.0f, 0.0f};
-        if (active) {
-            for (int cbi = cb_first; cbi < ncb; cbi += cb_step) {
-                const int cb = cbi * 32;
-                uint32_t v[32];
-                tmem_ld32(t_row + cb, v);
-                tmem_ld_wait();
-                if (!pix_ok) continue;
-                float f[32];
-#pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    float x = fmaf(__uint_as_float(v[c]), s_par[cb + c], s_par[C + cb + c]);
-                    if (e.act == 1) x = fmaxf(x, 0.0f);
-                    else if (e.act == 2) x = x > 0.0f ? x : 0.2f * x;
-                    if (e.scale2) x = fmaf(x, s_par[2 * C + cb + c], s_par[3 * C + cb + c]);
-                    f[c] = x;
-                }
-                if (e.resid_in) {
-                    const float4* rp = reinterpret_cast<const float4*>(e.resid + opix * C + cb);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const float4 rv = rp[c];
-                        f[4 * c] += rv.x; f[4 * c + 1] += rv.y; f[4 * c + 2] += rv.z; f[4 * c + 3] += rv.w;
-                    }
-                }
-                if (e.resid_out) {
-                    float4* rp = reinterpret_cast<float4*>(e.resid + opix * C + cb);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) rp[c] = make_float4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]);
-                }
-                if (e.out2_hi) {
-                    uint4* o = reinterpret_cast<uint4*>(e.out2_hi + opix * e.out2_pitch + e.out2_choff + cb);
-                    uint4* ol = e.out2_lo ? reinterpret_cast<uint4*>(e.out2_lo + opix * e.out2_pitch + e.out2_choff + cb) : nullptr;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        uint4 hi, lo;
-                        split8(f + 8 * c, hi, lo);
-                        o[c] = hi;
-                        if (ol) ol[c] = lo;
-                    }
-                }
-                if (e.out_relu) {
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) f[c] = fmaxf(f[c], 0.0f);
-                }
-                if (e.out_hi) {
-                    uint4* o = reinterpret_cast<uint4*>(e.out_hi + opix * e.out_pitch + e.out_choff + cb);
-                    uint4* ol = e.out_lo ? reinterpret_cast<uint4*>(e.out_lo + opix * e.out_pitch + e.out_choff + cb) : nullptr;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        uint4 hi, lo;
-                        split8(f + 8 * c, hi, lo);
-                        o[c] = hi;
-                        if (ol) ol[c] = lo;
-                    }
-                }
-                if (tail) {
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        y3[0] = fmaf(f[c], s_par[4 * C + cb + c], y3[0]);
-                        y3[1] = fmaf(f[c], s_par[5 * C + cb + c], y3[1]);
-                        y3[2] = fmaf(f[c], s_par[6 * C + cb + c], y3[2]);
-                    }
-                }
-            }
-            if (tail && pix_ok) {
-                const size_t plane = static_cast<size_t>(p.Hout) * p.Wout;
-                const size_t pin = static_cast<size_t>(oy) * p.Wout + oxe;
-                uint8_t rgb[3];
-#pragma unroll
-                for (int o = 0; o < 3; ++o) {
-                    float yv = y3[o] + s_par[7 * C + o];
-                    if (e.tanh_flag) yv = tanhf(yv);
-                    if (e.y_nchw) e.y_nchw[(static_cast<size_t>(n) * 3 + o) * plane + pin] = yv;
-                    rgb[o] = to_u8(yv);
-                }
-                if (e.y_rgba) {
-                    const uint8_t a = e.alpha_src ? e.alpha_src[opix * e.alpha_stride] : 255;
-                    reinterpret_cast<uchar4*>(e.y_rgba)[opix] = make_uchar4(rgb[0], rgb[1], rgb[2], a);
-                }
-            }
+        {
+            const int quad = warp & 3;
+            const int r = quad * 32 + lane;      // accumulator row = TMEM lane = patch pixel
+            epilogue_row(p, s_par, tmem_base + (static_cast<uint32_t>(quad * 32) << 16), n, ty0 + (r >> 4), tx0 + (r & 15), warp >> 2,
+                         kRic ? p.ks : 1, C);
         }
         tc_fence_before();
-    } else if (warp == 8) {
-        // ======================================================== MMA issuer (one thread)
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_f16(kTileM, C);
-            uint32_t acc = 0;
-            for (int q = 0; q < p.nchunks; ++q) {
-                const int s_a = q % SA, s_b = q % SB;
-                const ChunkHdr h = s_hdr[q];
-                mbar_wait(bar_full_b + 8 * s_b, (q / SB) & 1);
-                mbar_wait(bar_full_a + 8 * s_a, (q / SA) & 1);
-                tc_fence_after();
-                const uint32_t a_addr = base + L.a0 + s_a * kABytes;
-                const uint32_t b_addr = base + L.b0 + s_b * p.b_bytes;
+    } else if (warp < 8 + (kRic ? kIssuersRic : kIssuersTap)) {   // (idle issuer warps fall through)
+        // ======================================================== MMA issuers
+        // Warp-uniform loops (loop counters, launch constants) and one elected lane issues: keeps the
+        // descriptors in uniform registers (a divergent single-lane loop makes the compiler wrap every
+        // UTCHMMA in an R2UR / ELECT / BRA.U.ANY sequence).  One warp sustains only ~100 cycles per MMA
+        // (tools/umma_rate.cu), so RIC splits the 9 taps of every block over 3 issuers (tap % 3) that
+        // accumulate into separate TMEM column ranges, summed in the epilogue.
+        // The number of RIC issuers (p.ks, 1..3) is chosen by the planner so that every issuer owns a private
+        // weight ring of >= 2 stages: a ring shared by several consumers would let a warp that is one ring
+        // revolution ahead pass mbarrier.try_wait.parity on the previous phase.
+        const int NI = kRic ? p.ks : 1;
+        const int SBK = SB / NI;
+        const int wi = warp - 8;
+        if (wi < NI) {
+        const uint32_t idesc = umma_idesc_f16(kTileM, C);
+        const uint32_t d_addr = tmem_base + static_cast<uint32_t>(wi * C);
+        const int tail_from = kRic ? (p.nblocks - 1) * 9 : p.nchunks - 1;
+        uint32_t acc = 0;
+        int cnt = 0;
+        for (int q = 0; q < p.nchunks; ++q) {
+            if (kRic && (q % 9) % NI != wi) continue;
+            const int s_a = q % SA;
+            const int s_b = wi * SBK + cnt % SBK;
+            const uint32_t b_par = (cnt / SBK) & 1;
+            ++cnt;
+            const uint32_t km = q >= tail_from ? p.kmask_last : p.kmask_full;
+            const uint32_t km2 = q >= tail_from ? p.kmask2_last : p.kmask2_full;
+            mbar_wait(bar_full_b + 8 * s_b, b_par);
+            mbar_wait(bar_full_a + 8 * s_a, (q / SA) & 1);
+            tc_fence_after();
+            const uint32_t a_addr = base + L.a0 + s_a * kABytes;
+            const uint32_t b_addr = base + L.b0 + s_b * p.b_bytes;
+            if (elect_one()) {
+                const uint64_t da0 = umma_desc_sw128(a_addr, 1024), db0 = umma_desc_sw128(b_addr, 1024);
+                if (km == 0xFu) {
+                    umma_f16(d_addr, da0, db0, idesc, acc);
+                    umma_f16(d_addr, da0 + 2, db0 + 2, idesc, 1u);
+                    umma_f16(d_addr, da0 + 4, db0 + 4, idesc, 1u);
+                    umma_f16(d_addr, da0 + 6, db0 + 6, idesc, 1u);
+                } else {
+                    uint32_t a2 = acc;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if ((h.kmask >> k) & 1) {
-                        umma_f16(tmem_base, umma_desc_sw128(a_addr + k * 32, 1024), umma_desc_sw128(b_addr + k * 32, 1024), idesc, acc);
-                        acc = 1;
-                    }
+                    for (int k = 0; k < 4; ++k)
+                        if ((km >> k) & 1) { umma_f16(d_addr, da0 + 2 * k, db0 + 2 * k, idesc, a2); a2 = 1u; }
+                }
+                if (km2) {
+                    const uint64_t db1 = umma_desc_sw128(b_addr + C * 128, 1024);
 #pragma unroll
-                for (int k = 0; k < 2; ++k)
-                    if ((h.kmask2 >> k) & 1)
-                        umma_f16(tmem_base, umma_desc_sw128(a_addr + k * 32, 1024),
-                                 umma_desc_sw128(b_addr + C * 128 + k * 32, 1024), idesc, 1u);
+                    for (int k = 0; k < 2; ++k)
+                        if ((km2 >> k) & 1) umma_f16(d_addr, da0 + 2 * k, db1 + 2 * k, idesc, 1u);
+                }
                 umma_commit(bar_empty_a + 8 * s_a);      // frees the stages when these MMAs retire
                 umma_commit(bar_empty_b + 8 * s_b);
             }
-            umma_commit(bar_accum);                      // accumulator complete -> epilogue
+            acc = 1u;
+            __syncwarp();
         }
+        if (elect_one()) umma_commit(bar_accum);         // this issuer's partial accumulator is complete
         __syncwarp();
+        }
         tc_fence_before();
     } else {
-        // ======================================================== weight (B operand) loader
-        if (lane == 0) {
-            for (int q = 0; q < p.nchunks; ++q) {
-                const int s = q % SB;
-                if (q >= SB) mbar_wait(bar_empty_b + 8 * s, ((q / SB) - 1) & 1);
-                const ChunkHdr h = s_hdr[q];
-                const uint32_t bytes = static_cast<uint32_t>(h.kmask2 ? 2 * C : C) * 128u;
-                mbar_arrive_expect_tx(bar_full_b + 8 * s, bytes);
-                bulk_g2s(base + L.b0 + s * p.b_bytes, p.wpack + h.b_off, bytes, bar_full_b + 8 * s);
+        // ======================================================== weight (B operand) loader: chunk q -> ring of its issuer
+        const int NI = kRic ? p.ks : 1;
+        const int SBK = SB / NI;
+        int cnt[kIssuersRic] = {0, 0, 0};
+        for (int q = 0; q < p.nchunks; ++q) {
+            const int k = kRic ? (q % 9) % NI : 0;
+            int c = 0;
+#pragma unroll
+            for (int i = 0; i < kIssuersRic; ++i) if (i == k) { c = cnt[i]; cnt[i] = c + 1; }
+            const int s = k * SBK + c % SBK;
+            if (c >= SBK) mbar_wait(bar_empty_b + 8 * s, ((c / SBK) - 1) & 1);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(bar_full_b + 8 * s, static_cast<uint32_t>(p.b_bytes));
+                bulk_g2s(base + L.b0 + s * p.b_bytes, p.wpack + static_cast<size_t>(q) * p.b_bytes,
+                         static_cast<uint32_t>(p.b_bytes), bar_full_b + 8 * s);
             }
+            __syncwarp();
         }
-        __syncwarp();
     }
 
     __syncthreads();
@@ -473,12 +377,12 @@ cudaError_t launch_conv(const ConvParams& p, cudaStream_t stream) {
         if (e != cudaSuccess) return e;
         attr_set[dev] = true;
     }
-    if (p.sa < 2 || p.sa > kMaxStagesA || p.sb < 2 || p.sb > kMaxStagesB || (p.ric && p.sa != 9) ||
+    if (p.sa < 2 || p.sa > kMaxStagesA || p.sb < 2 || p.sb > kMaxStagesB || (p.ric && (p.sa != 9 || p.ks < 1 || p.ks > kIssuersRic || p.sb / p.ks < 2)) ||
         conv_smem_bytes(p) > 227 * 1024)
         return cudaErrorInvalidConfiguration;
     dim3 grid((p.Wout + kTileW - 1) / kTileW, (p.Hout + kTileH - 1) / kTileH, p.B);
-    if (p.ric) conv_umma_kernel<true><<<grid, kThreads, conv_smem_bytes(p), stream>>>(p);
-    else conv_umma_kernel<false><<<grid, kThreads, conv_smem_bytes(p), stream>>>(p);
+    if (p.ric) conv_umma_kernel<true><<<grid, kThreadsRic, conv_smem_bytes(p), stream>>>(p);
+    else conv_umma_kernel<false><<<grid, kThreadsTap, conv_smem_bytes(p), stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <set>
@@ -53,8 +54,10 @@ struct LayerDef {
     int act = 0;
     int out_buf = -1, out_choff = 0, out_relu = 0, out2_buf = -1;
     int resid_in = 0, resid_out = 0, final = 0;
+    int halo = 0;          // plain stride-1 conv run by the halo-reuse kernel (conv_halo.cu)
     // compiled at finalize
     int nchunks = 0, nblocks = 0;
+    uint32_t kmask_full = 0xF, kmask_last = 0xF, kmask2_full = 0, kmask2_last = 0;
     Slot* d_slots = nullptr;
     ChunkHdr* d_hdrs = nullptr;
     uint8_t* d_wpack = nullptr;
@@ -288,7 +291,8 @@ int compile_layer(dsu_engine* E, LayerDef& L) {
             else slots.push_back(Slot{});
         }
     };
-    if (!L.ric) {
+    L.halo = (!L.ric && L.stride == 1 && real_k / (k * k) >= 32) ? 1 : 0;
+    if (!L.ric && !L.halo) {
         std::vector<HSlot> all;
         for (int kh = 0; kh < k; ++kh)
             for (int kw = 0; kw < k; ++kw)
@@ -314,9 +318,9 @@ int compile_layer(dsu_engine* E, LayerDef& L) {
         for (int b = 0; b < L.nblocks; ++b) {
             std::vector<HSlot> blk(groups.begin() + b * dpc, groups.begin() + std::min<size_t>(groups.size(), (b + 1) * dpc));
             push_dev_slots(blk);                               // one slot row per BLOCK
-            for (int tap = 0; tap < 9; ++tap) {
+            for (int tap = 0; tap < k * k; ++tap) {
                 std::vector<HSlot> ds = blk;
-                for (HSlot& h : ds) { h.kh = tap / 3; h.kw = tap % 3; }
+                for (HSlot& h : ds) { h.kh = tap / k; h.kw = tap % k; }
                 chunks.push_back(ds);
             }
         }
@@ -356,6 +360,8 @@ int compile_layer(dsu_engine* E, LayerDef& L) {
         off += tile * (exact ? 2 : 1);
     }
     pack.resize(off);
+    L.kmask_full = hdrs.front().kmask; L.kmask2_full = hdrs.front().kmask2;
+    L.kmask_last = hdrs.back().kmask; L.kmask2_last = hdrs.back().kmask2;
     int rc;
     if ((rc = upload(&L.d_slots, slots))) return rc;
     if ((rc = upload(&L.d_hdrs, hdrs))) return rc;
@@ -541,9 +547,16 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
         p.stride = L.stride; p.ric = L.ric; p.exact = E->exact ? 1 : 0;
         p.nchunks = L.nchunks; p.nblocks = L.nblocks; p.Cout = L.cout;
         p.b_bytes = (E->exact ? 2 : 1) * L.cout * 128;
+        p.kmask_full = L.kmask_full; p.kmask_last = L.kmask_last; p.kmask2_full = L.kmask2_full; p.kmask2_last = L.kmask2_last;
         pick_stages(L.ric != 0, p.b_bytes, &p.sa, &p.sb);
+        p.ks = 1;
+        if (L.ric) {   // K-split issuers: each needs a private weight ring of >= 2 stages and a TMEM accumulator
+            p.ks = std::max(1, std::min(kIssuersRic, std::min(p.sb / 2, 512 / L.cout)));
+            if (const char* ev = std::getenv("DSU_RIC_KS")) p.ks = std::max(1, std::min(p.ks, std::atoi(ev)));
+            p.sb = (p.sb / p.ks) * p.ks;
+        }
         int cols = 32;
-        while (cols < L.cout) cols *= 2;
+        while (cols < p.ks * L.cout) cols *= 2;
         p.tmem_cols = cols;
         p.slots = L.d_slots; p.hdrs = L.d_hdrs; p.wpack = L.d_wpack;
         for (size_t i = 0; i < L.segs.size(); ++i) {
@@ -568,7 +581,41 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
             e.w12 = E->d_w12; e.b12 = E->d_b12; e.tanh_flag = E->cfg.tanh;
             e.y_nchw = y_dev; e.y_rgba = y_rgba; e.alpha_src = alpha_src; e.alpha_stride = alpha_stride;
         }
-        CUDA_TRY(launch_conv(p, st));
+        if (L.halo) {
+            // ns sub-tiles x ks K-split issuers (<= 4 issuing warps, <= 512 TMEM columns); shared memory:
+            // 2 halo buffers + as many weight stages as fit
+            p.halo = 1; p.ksize = L.k; p.pad = L.pad;
+            // candidates in order of measured preference (profiles/r01d sweep): wide CTAs for 3x3 (weight-tile reuse),
+            // sub-tile x K-split for 7x7 (halo size); the first that fits TMEM and shared memory wins
+            static const int cand3[][2] = {{4, 1}, {2, 2}, {2, 1}, {1, 2}, {1, 1}};
+            static const int cand7[][2] = {{2, 2}, {2, 1}, {1, 2}, {1, 1}, {1, 1}};
+            const int (*cand)[2] = L.k == 3 ? cand3 : cand7;
+            int env_ns = 0, env_ks = 0;
+            if (const char* ev = std::getenv("DSU_HALO_NS")) env_ns = std::max(1, std::min(4, std::atoi(ev)));
+            if (const char* ev = std::getenv("DSU_HALO_KS")) env_ks = std::max(1, std::min(4, std::atoi(ev)));
+            bool found = false;
+            for (int ci = 0; ci < 5 && !found; ++ci) {
+                const int ns = env_ns ? env_ns : cand[ci][0], ks = env_ks ? env_ks : cand[ci][1];
+                if (ns * ks > kIssuersHalo || ns * ks * L.cout > 512 || ks > L.k * L.k) continue;
+                p.ns = ns; p.ks = ks;
+                p.halo_w = 8 * ns + 2 * L.pad;
+                p.halo_rows = (16 + 2 * L.pad) * p.halo_w;
+                p.halo_bytes = (p.halo_rows * 128 + 1023) & ~1023;
+                p.sa = 2;
+                const int left = 227 * 1024 - 2 * p.halo_bytes - 8 * 1024;
+                p.sb = std::min(kMaxStagesB, left / p.b_bytes);
+                if (const char* ev = std::getenv("DSU_HALO_SB")) p.sb = std::max(2, std::min(p.sb, std::atoi(ev)));
+                p.sb = (p.sb / ks) * ks;
+                found = p.sb / ks >= 2;
+            }
+            if (!found) return fail(DSU_E_INVALID, "halo convolution does not fit in shared memory: " + L.name);
+            cols = 32;
+            while (cols < p.ns * p.ks * L.cout) cols *= 2;
+            p.tmem_cols = cols;
+            CUDA_TRY(launch_conv_halo(p, st));
+        } else {
+            CUDA_TRY(launch_conv(p, st));
+        }
     }
     if (evs) CUDA_TRY(cudaEventRecord((*evs)[step_idx], st));
     return DSU_OK;
