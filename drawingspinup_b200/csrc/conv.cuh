@@ -17,7 +17,7 @@ constexpr int kWorkers = 256;   // producer / epilogue threads (warps 0-7)
 // with its own TMEM accumulator (sub-tile and/or K split; partial sums are added in the epilogue).
 constexpr int kIssuersTap = 1;   // tap-mode plain conv
 constexpr int kIssuersRic = 3;   // RIC: taps t with t % 3 == issuer
-constexpr int kIssuersHalo = 4;  // halo: ns sub-tiles x ks K-splits <= 4
+constexpr int kIssuersHalo = 4;  // halo: ns sub-tiles x ks K-splits <= 4 (8 issuers with 4 worker warps measured slower)
 constexpr int kThreadsTap = (8 + kIssuersTap + 1) * 32;
 constexpr int kThreadsRic = (8 + kIssuersRic + 1) * 32;
 constexpr int kThreadsHalo = (8 + kIssuersHalo + 1) * 32;

@@ -57,14 +57,14 @@ __device__ __forceinline__ void load_epilogue_params(const ConvParams& p, float*
 // warp-collective); chalf is warp-uniform.
 // `nsplit` partial accumulators `split_stride` columns apart (K-split issuers) are summed first.
 __device__ __forceinline__ void epilogue_row(const ConvParams& p, const float* s_par, uint32_t t_addr,
-                                             int n, int oy, int ox, int chalf, int nsplit = 1, int split_stride = 0) {
+                                             int n, int oy, int ox, int chalf, int nsplit = 1, int split_stride = 0, int csplit = 2) {
     const EpiParams& e = p.epi;
     const int C = p.Cout;
     const bool pix_ok = oy < p.Hout && ox < p.Wout;
     const size_t opix = (static_cast<size_t>(n) * p.Hout + oy) * p.Wout + ox;
     const int ncb = C / 32;
     const bool tail = e.w12 != nullptr;
-    const int cb_first = tail ? 0 : chalf, cb_step = tail ? 1 : 2;
+    const int cb_first = tail ? 0 : chalf, cb_step = tail ? 1 : csplit;   // csplit warps share a lane quadrant
     const bool active = tail ? (chalf == 0) : (chalf < ncb);
     if (!active) return;
     float y3[3] = {0.0f, 0.0f, 0.0f};

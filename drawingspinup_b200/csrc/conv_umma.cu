@@ -21,6 +21,7 @@
 // [W_hi | W_hi] (4 K-steps) and its hi half again by W_lo (2 K-steps) into the same accumulator:
 // a_hi*W_hi + a_lo*W_hi + a_hi*W_lo, fp32-grade products at 3x the tensor work.
 #include "conv_device.cuh"
+#include "ric_producer.cuh"
 
 namespace dsu {
 
@@ -44,16 +45,13 @@ __host__ __device__ inline SmemLayout smem_layout(int sa, int sb, int b_bytes, i
     return L;
 }
 
-// Static corner set of rotated tap m (sample angle in [m*45, m*45+45) degrees):
-// row offset cos<0 for m in 2..5, column offset sin<0 for m in 4..7.
-__device__ __forceinline__ constexpr int quad_r0(int m) { return (m >= 2 && m <= 5) ? 0 : 1; }
-__device__ __forceinline__ constexpr int quad_c0(int m) { return (m >= 4) ? 0 : 1; }
-
 }  // namespace
 
-template <bool kRic>
-__global__ void __launch_bounds__(kRic ? kThreadsRic : kThreadsTap, kRic ? 1 : 2)
+// kMode: 0 = tap-mode plain conv, 1 = RIC (fp16), 2 = RIC (split fp16 hi|lo)
+template <int kMode>
+__global__ void __launch_bounds__(kMode ? kThreadsRic : kThreadsTap, kMode ? 1 : 2)
 conv_umma_kernel(const __grid_constant__ ConvParams p) {
+    constexpr bool kRic = kMode != 0;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_u32 = smem_u32(smem_raw);
     const uint32_t base = (raw_u32 + 1023u) & ~1023u;
@@ -145,122 +143,8 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             for (int q = (p.nchunks > LAG ? p.nchunks - LAG : 0); q < p.nchunks; ++q)
                 mbar_arrive(bar_full_a + 8 * (q % SA));
         } else {
-            // ---- RIC: one (pixel, 8-channel group) item = 9 neighbour loads -> 8 blended taps + centre.
-            // chunk q = block * 9 + tap lives in A buffer `tap` (SA == 9).
-            const bool exact = p.exact != 0;
-            const int cg = exact ? (j & 3) : j;                 // data slot handled by this thread
-            const int i_lo = exact ? 2 * (j >> 2) : 0;          // exact: the two threads of a slot pair split the rows
-            const int i_hi = exact ? i_lo + 2 : 4;
-            const uint32_t slot_hi = static_cast<uint32_t>(cg ^ swz) << 4;
-            const uint32_t slot_lo = static_cast<uint32_t>((cg + 4) ^ swz) << 4;
-            for (int b = 0; b < p.nblocks; ++b) {
-                const Slot sl = p.slots[b * 8 + cg];
-                const Seg sg = p.seg[sl.seg];
-                const __half* sbase = sg.ptr + sl.choff;
-                const __half* sbase_lo = exact ? p.seg[sl.seg + kMaxSeg / 2].ptr + sl.choff : nullptr;
-                for (int i = i_lo; i < i_hi; ++i) {
-                    const int r = prow + 32 * i;
-                    const int oy = ty0 + (r >> 4), ox = tx0 + (r & 15);
-                    const bool live = sl.valid && oy < p.Hout && ox < p.Wout;
-                    // ---- stencil of this pixel
-                    float2 lyx[8];
-                    int oct = 0;
-                    if (live) {
-                        const size_t e = static_cast<size_t>(oy) * p.Wout + ox;
-                        const float4* tp = reinterpret_cast<const float4*>(p.ric_lyx + e * 8);
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            const float4 v = __ldg(tp + t);
-                            lyx[2 * t] = make_float2(v.x, v.y);
-                            lyx[2 * t + 1] = make_float2(v.z, v.w);
-                        }
-                        oct = __ldg(p.ric_oct + e);
-                    } else {
-#pragma unroll
-                        for (int t = 0; t < 8; ++t) lyx[t] = make_float2(0.0f, 0.0f);
-                    }
-                    // ---- 3x3 neighbourhood (virtual coordinates; nearest-x2 folded into the address)
-                    uint4 nb[9], nbl[9];
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) {
-                        const int vy = oy + k / 3 - 1, vx = ox + k % 3 - 1;
-                        const bool inb = live && static_cast<unsigned>(vy) < static_cast<unsigned>(p.Hv) &&
-                                         static_cast<unsigned>(vx) < static_cast<unsigned>(p.Wv);
-                        nb[k] = make_uint4(0, 0, 0, 0);
-                        nbl[k] = make_uint4(0, 0, 0, 0);
-                        if (inb) {
-                            const size_t pix = frame_in + static_cast<size_t>(vy >> p.up) * p.Win + (vx >> p.up);
-                            nb[k] = __ldg(reinterpret_cast<const uint4*>(sbase + pix * sg.pitch));
-                            if (exact) nbl[k] = __ldg(reinterpret_cast<const uint4*>(sbase_lo + pix * sg.pitch));
-                        }
-                    }
-                    // first item of a block: the previous block's MMAs must have drained the tap buffers
-                    if (b > 0 && i == i_lo) {
-#pragma unroll 1
-                        for (int t = 0; t < 9; ++t) mbar_wait(bar_empty_a + 8 * t, (b - 1) & 1);
-                    }
-                    uint8_t* rowp = smem + L.a0 + r * 128;
-                    // ---- centre tap (raster tap 4): the pixel itself
-                    *reinterpret_cast<uint4*>(rowp + 4 * kABytes + slot_hi) = nb[4];
-                    if (exact) *reinterpret_cast<uint4*>(rowp + 4 * kABytes + slot_lo) = nbl[4];
-                    // ---- 8 circle taps, two channel halves to bound register use
-                    uint32_t keep[8][2];       // half-0 results (packed) while half 1 is computed
-                    float keepf[8][4];         // exact mode keeps fp32 to split hi/lo over all 8 channels
-#pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {
-                        float nf[9][4];
-#pragma unroll
-                        for (int k = 0; k < 9; ++k) {
-                            const float2 a = unpack_h2(hf ? nb[k].z : nb[k].x), c = unpack_h2(hf ? nb[k].w : nb[k].y);
-                            nf[k][0] = a.x; nf[k][1] = a.y; nf[k][2] = c.x; nf[k][3] = c.y;
-                            if (exact) {
-                                const float2 al = unpack_h2(hf ? nbl[k].z : nbl[k].x), cl = unpack_h2(hf ? nbl[k].w : nbl[k].y);
-                                nf[k][0] += al.x; nf[k][1] += al.y; nf[k][2] += cl.x; nf[k][3] += cl.y;
-                            }
-                        }
-#pragma unroll
-                        for (int m = 0; m < 8; ++m) {
-                            const float ly = lyx[m].x, lx = lyx[m].y;
-                            const float hy = 1.0f - ly, hx = 1.0f - lx;
-                            const float w00 = hy * hx, w01 = hy * lx, w10 = ly * hx, w11 = ly * lx;
-                            const int r0 = quad_r0(m), c0 = quad_c0(m);
-                            float o[4];
-#pragma unroll
-                            for (int c = 0; c < 4; ++c)
-                                o[c] = fmaf(w11, nf[(r0 + 1) * 3 + c0 + 1][c],
-                                       fmaf(w10, nf[(r0 + 1) * 3 + c0][c],
-                                       fmaf(w01, nf[r0 * 3 + c0 + 1][c], w00 * nf[r0 * 3 + c0][c])));
-                            if (hf == 0) {
-                                if (exact) {
-#pragma unroll
-                                    for (int c = 0; c < 4; ++c) keepf[m][c] = o[c];
-                                } else {
-                                    keep[m][0] = pack_h2(o[0], o[1]);
-                                    keep[m][1] = pack_h2(o[2], o[3]);
-                                }
-                            } else {
-                                const int kq = (m - oct) & 7;               // reference rotation index of this tap
-                                const int tap = kq + (kq >= 4 ? 1 : 0);     // raster tap -> A buffer
-                                uint8_t* dst = rowp + tap * kABytes;
-                                if (exact) {
-                                    const float f8[8] = {keepf[m][0], keepf[m][1], keepf[m][2], keepf[m][3], o[0], o[1], o[2], o[3]};
-                                    uint4 hi, lo;
-                                    split8(f8, hi, lo);
-                                    *reinterpret_cast<uint4*>(dst + slot_hi) = hi;
-                                    *reinterpret_cast<uint4*>(dst + slot_lo) = lo;
-                                } else {
-                                    uint4 v;
-                                    v.x = keep[m][0]; v.y = keep[m][1]; v.z = pack_h2(o[0], o[1]); v.w = pack_h2(o[2], o[3]);
-                                    *reinterpret_cast<uint4*>(dst + slot_hi) = v;
-                                }
-                            }
-                        }
-                    }
-                }
-                fence_proxy_async_smem();
-#pragma unroll 1
-                for (int t = 0; t < 9; ++t) mbar_arrive(bar_full_a + 8 * t);
-            }
+            // ---- RIC: 3x3 neighbourhood -> 8 blended circle taps + centre, one A buffer per tap (ric_producer.cuh)
+            ric_produce<kMode == 2>(p, smem + L.a0, bar_full_a, bar_empty_a, tid, n, ty0, tx0);
         }
 
         // ======================================================== epilogue (warps 0-7)
@@ -371,9 +255,11 @@ cudaError_t launch_conv(const ConvParams& p, cudaStream_t stream) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 64 && !attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        e = cudaFuncSetAttribute(conv_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(conv_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_set[dev] = true;
     }
@@ -381,8 +267,9 @@ cudaError_t launch_conv(const ConvParams& p, cudaStream_t stream) {
         conv_smem_bytes(p) > 227 * 1024)
         return cudaErrorInvalidConfiguration;
     dim3 grid((p.Wout + kTileW - 1) / kTileW, (p.Hout + kTileH - 1) / kTileH, p.B);
-    if (p.ric) conv_umma_kernel<true><<<grid, kThreadsRic, conv_smem_bytes(p), stream>>>(p);
-    else conv_umma_kernel<false><<<grid, kThreadsTap, conv_smem_bytes(p), stream>>>(p);
+    if (p.ric && p.exact) conv_umma_kernel<2><<<grid, kThreadsRic, conv_smem_bytes(p), stream>>>(p);
+    else if (p.ric) conv_umma_kernel<1><<<grid, kThreadsRic, conv_smem_bytes(p), stream>>>(p);
+    else conv_umma_kernel<0><<<grid, kThreadsTap, conv_smem_bytes(p), stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -40,7 +40,7 @@ int fail(int code, const std::string& msg) {
             return fail(DSU_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));      \
     } while (0)
 
-enum BufId { SK0 = 0, P0, O1, P1, O2, TT, UU, V2, V1, C11, S0, NBUF };
+enum BufId { SK0 = 0, P0, O1, P1, O2, TT, UU, V2, V1, C11, S0, EXP0, NBUF };
 
 struct SegDef {
     int buf, choff, nch;   // buffer, first channel, channels consumed (multiple of 8)
@@ -55,6 +55,7 @@ struct LayerDef {
     int out_buf = -1, out_choff = 0, out_relu = 0, out2_buf = -1;
     int resid_in = 0, resid_out = 0, final = 0;
     int halo = 0;          // plain stride-1 conv run by the halo-reuse kernel (conv_halo.cu)
+    int expanded = 0;      // stage-1 conv0: the 9 RIC taps were materialised by ric_expand -> 1x1 contraction
     // compiled at finalize
     int nchunks = 0, nblocks = 0;
     uint32_t kmask_full = 0xF, kmask_last = 0xF, kmask2_full = 0, kmask2_last = 0;
@@ -66,7 +67,7 @@ struct LayerDef {
 };
 
 struct Step {
-    int type;    // 0 conv, 1 maxpool
+    int type;    // 0 conv, 1 maxpool, 2 RIC tap expansion of the network input
     int layer;
     int src, src_choff, C, dst;
 };
@@ -166,7 +167,7 @@ int build_plan(dsu_engine* E) {
     setbuf(SK0, 0, f[0] + cp);
     setbuf(O1, 1, f[1]);
     setbuf(O2, 2, f[2]);
-    if (ric) { setbuf(P0, 1, f[0]); setbuf(P1, 2, f[1]); }
+    if (ric) { setbuf(P0, 1, f[0]); setbuf(P1, 2, f[1]); setbuf(EXP0, 0, 9 * cp); }
     if (c.resnet_blocks > 0) { setbuf(TT, 2, f[2]); setbuf(UU, 2, f[2]); }
     setbuf(V2, 1, f[4]);
     setbuf(V1, 0, f[4]);
@@ -180,6 +181,10 @@ int build_plan(dsu_engine* E) {
         LayerDef L; L.name = "conv0"; L.wkey = "conv0.conv.weight"; L.bkey = bias_of("conv0.conv");
         L.bn = bn ? "conv0.normalization" : ""; L.k = k0; L.pad = k0 / 2; L.ric = ric; L.cout = f[0]; L.level_out = 0;
         L.segs = {{SK0, f[0], cp, 0, cin}}; L.act = 2; L.out_buf = SK0; L.out_choff = 0;
+        if (ric) {   // sample the 9 taps of the 8-channel input once, then contract over 9 * cp channels
+            E->steps.push_back(Step{2, -1, SK0, f[0], cp, EXP0});
+            L.ric = 0; L.expanded = 1; L.segs = {{EXP0, 0, cp, 0, cin}};
+        }
         add(L);
     }
     if (ric) E->steps.push_back(Step{1, -1, SK0, 0, f[0], P0});
@@ -277,8 +282,8 @@ int compile_layer(dsu_engine* E, LayerDef& L) {
     L.macs_per_px = real_k * C;
     auto dev_slot = [&](const HSlot& h, bool lo_plane) {
         Slot sl{};
-        sl.dy = static_cast<int8_t>(h.kh - L.pad);
-        sl.dx = static_cast<int8_t>(h.kw - L.pad);
+        sl.dy = static_cast<int8_t>(L.expanded ? 0 : h.kh - L.pad);
+        sl.dx = static_cast<int8_t>(L.expanded ? 0 : h.kw - L.pad);
         sl.seg = static_cast<uint8_t>(h.seg + (lo_plane ? kMaxSeg / 2 : 0));
         sl.valid = 1;
         sl.choff = static_cast<uint16_t>(h.choff);
@@ -291,8 +296,22 @@ int compile_layer(dsu_engine* E, LayerDef& L) {
             else slots.push_back(Slot{});
         }
     };
-    L.halo = (!L.ric && L.stride == 1 && real_k / (k * k) >= 32) ? 1 : 0;
-    if (!L.ric && !L.halo) {
+    L.halo = (!L.ric && !L.expanded && L.stride == 1 && real_k / (k * k) >= 32) ? 1 : 0;
+    if (L.expanded) {
+        // data slot = (tap, 8-channel group) of the expanded buffer [pix][tap * nch + c]; weights keep their 3x3 index
+        L.halo = 0;
+        const SegDef& s0 = L.segs[0];
+        std::vector<HSlot> all;
+        for (int tap = 0; tap < k * k; ++tap)
+            for (int c8 = 0; c8 < s0.nch; c8 += 8)
+                all.push_back(HSlot{tap / k, tap % k, 0, tap * s0.nch + c8, s0.wch0 + c8, std::max(0, std::min(8, s0.wn - c8))});
+        for (size_t i = 0; i < all.size(); i += dpc) {
+            std::vector<HSlot> ds(all.begin() + i, all.begin() + std::min(all.size(), i + dpc));
+            push_dev_slots(ds);
+            chunks.push_back(ds);
+        }
+        L.nblocks = 0;
+    } else if (!L.ric && !L.halo) {
         std::vector<HSlot> all;
         for (int kh = 0; kh < k; ++kh)
             for (int kw = 0; kw < k; ++kw)
@@ -538,6 +557,11 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
                               E->buf_hi[sp.dst], E->buf_lo[sp.dst], E->buf_C[sp.dst], st));
             continue;
         }
+        if (sp.type == 2) {
+            CUDA_TRY(ric_expand(E->buf_hi[sp.src], E->buf_lo[sp.src], E->buf_C[sp.src], sp.src_choff, sp.C / 8, B, H, W,
+                                E->lv[0].lyx, E->lv[0].oct, E->buf_hi[sp.dst], E->buf_lo[sp.dst], st));
+            continue;
+        }
         const LayerDef& L = E->layers[sp.layer];
         ConvParams p{};
         p.B = B; p.Hout = H >> L.level_out; p.Wout = W >> L.level_out;
@@ -592,7 +616,7 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
             const int (*cand)[2] = L.k == 3 ? cand3 : cand7;
             int env_ns = 0, env_ks = 0;
             if (const char* ev = std::getenv("DSU_HALO_NS")) env_ns = std::max(1, std::min(4, std::atoi(ev)));
-            if (const char* ev = std::getenv("DSU_HALO_KS")) env_ks = std::max(1, std::min(4, std::atoi(ev)));
+            if (const char* ev = std::getenv("DSU_HALO_KS")) env_ks = std::max(1, std::min(8, std::atoi(ev)));
             bool found = false;
             for (int ci = 0; ci < 5 && !found; ++ci) {
                 const int ns = env_ns ? env_ns : cand[ci][0], ks = env_ks ? env_ks : cand[ci][1];
@@ -865,7 +889,7 @@ int dsu_profile_forward(dsu_handle h, int32_t B, int32_t H, int32_t W, int32_t r
 const char* dsu_step_name(dsu_handle h, int32_t index) {
     if (!h || index < 0 || index >= static_cast<int>(h->steps.size())) return "";
     const Step& sp = h->steps[index];
-    return sp.type == 0 ? h->layers[sp.layer].name.c_str() : "maxpool";
+    return sp.type == 0 ? h->layers[sp.layer].name.c_str() : (sp.type == 1 ? "maxpool" : "ric_expand");
 }
 
 int dsu_frames_to_tensor(const uint8_t* color_dev, const uint8_t* pos_dev, const uint8_t* edge_dev,

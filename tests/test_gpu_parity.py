@@ -306,8 +306,8 @@ def test_flop_model_and_launch_count(dev):
     m2, _ = _model(2, dev)
     assert abs(m1.algorithmic_flops(1, 512, 512) - 297.56e9) / 297.56e9 < 1e-3
     assert abs(m2.algorithmic_flops(1, 512, 512) - 543.72e9) / 543.72e9 < 1e-3
-    # ingest + fused convs (+ 2 max-pools in stage 1; its dead smoother conv is not launched)
-    assert m1.kernel_launches(1, 512, 512) == 1 + 21 + 2 and m2.kernel_launches(1, 512, 512) == 1 + 22
+    # ingest + fused convs (+ RIC tap expansion of the input and 2 max-pools in stage 1; its dead smoother conv is not launched)
+    assert m1.kernel_launches(1, 512, 512) == 1 + 21 + 3 and m2.kernel_launches(1, 512, 512) == 1 + 22
 
 
 def test_multi_gpu_shard_equivalence(dev):
