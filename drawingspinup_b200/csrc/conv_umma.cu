@@ -47,7 +47,7 @@ __host__ __device__ inline SmemLayout smem_layout(int sa, int sb, int b_bytes, i
 
 }  // namespace
 
-// kMode: 0 = tap-mode plain conv, 1 = RIC (fp16), 2 = RIC (split fp16 hi|lo)
+// kMode: 0 = tap-mode plain conv, 1 = RIC (fp16, fp32 blend), 2 = RIC (split fp16 hi|lo), 3 = RIC (fp16, packed half2 blend)
 template <int kMode>
 __global__ void __launch_bounds__(kMode ? kThreadsRic : kThreadsTap, kMode ? 1 : 2)
 conv_umma_kernel(const __grid_constant__ ConvParams p) {
@@ -144,7 +144,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                 mbar_arrive(bar_full_a + 8 * (q % SA));
         } else {
             // ---- RIC: 3x3 neighbourhood -> 8 blended circle taps + centre, one A buffer per tap (ric_producer.cuh)
-            ric_produce<kMode == 2>(p, smem + L.a0, bar_full_a, bar_empty_a, tid, n, ty0, tx0);
+            ric_produce<kMode == 2, kMode == 3>(p, smem + L.a0, bar_full_a, bar_empty_a, tid, n, ty0, tx0);
         }
 
         // ======================================================== epilogue (warps 0-7)
@@ -261,6 +261,8 @@ cudaError_t launch_conv(const ConvParams& p, cudaStream_t stream) {
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(conv_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(conv_umma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
         attr_set[dev] = true;
     }
     if (p.sa < 2 || p.sa > kMaxStagesA || p.sb < 2 || p.sb > kMaxStagesB || (p.ric && (p.sa != 9 || p.ks < 1 || p.ks > kIssuersRic || p.sb / p.ks < 2)) ||
@@ -268,6 +270,7 @@ cudaError_t launch_conv(const ConvParams& p, cudaStream_t stream) {
         return cudaErrorInvalidConfiguration;
     dim3 grid((p.Wout + kTileW - 1) / kTileW, (p.Hout + kTileH - 1) / kTileH, p.B);
     if (p.ric && p.exact) conv_umma_kernel<2><<<grid, kThreadsRic, conv_smem_bytes(p), stream>>>(p);
+    else if (p.ric == 2) conv_umma_kernel<3><<<grid, kThreadsRic, conv_smem_bytes(p), stream>>>(p);
     else if (p.ric) conv_umma_kernel<1><<<grid, kThreadsRic, conv_smem_bytes(p), stream>>>(p);
     else conv_umma_kernel<0><<<grid, kThreadsTap, conv_smem_bytes(p), stream>>>(p);
     return cudaGetLastError();

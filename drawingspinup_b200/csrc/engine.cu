@@ -569,6 +569,8 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
         p.Hin = H >> src_level; p.Win = W >> src_level;
         p.up = L.up; p.Hv = p.Hin << L.up; p.Wv = p.Win << L.up;
         p.stride = L.stride; p.ric = L.ric; p.exact = E->exact ? 1 : 0;
+        // fp16 mode blends the RIC taps with packed half2 math unless DSU_RIC_FP32_BLEND=1 (p.ric == 2 selects it)
+        if (L.ric && !E->exact && !std::getenv("DSU_RIC_FP32_BLEND")) p.ric = 2;
         p.nchunks = L.nchunks; p.nblocks = L.nblocks; p.Cout = L.cout;
         p.b_bytes = (E->exact ? 2 : 1) * L.cout * 128;
         p.kmask_full = L.kmask_full; p.kmask_last = L.kmask_last; p.kmask2_full = L.kmask2_full; p.kmask2_last = L.kmask2_last;

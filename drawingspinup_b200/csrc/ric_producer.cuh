@@ -18,7 +18,8 @@ __device__ __forceinline__ constexpr int ric_c0(int m) { return (m >= 4) ? 0 : 1
 // kExact = false: 256 threads = 32 pixel rows x 8 slots, 4 items per thread, fp16 result.
 // kExact = true : slots are [hi x4 | lo x4]; thread (prow, j) handles channel group j & 3 for two of the
 //                 four pixel rows, reads hi + lo planes and writes fp16 hi and lo = fp16(v - hi).
-template <bool kExact>
+// kHalfBlend (fp16 mode only): blend with packed half2 math instead of fp32.
+template <bool kExact, bool kHalfBlend>
 __device__ __forceinline__ void ric_produce(const ConvParams& p, uint8_t* a_smem, uint32_t bar_full_a, uint32_t bar_empty_a,
                                             int tid, int n, int ty0, int tx0) {
     const int j = tid & 7, prow = tid >> 3, swz = prow & 7;
@@ -44,13 +45,14 @@ __device__ __forceinline__ void ric_produce(const ConvParams& p, uint8_t* a_smem
         const int pitch = sg.pitch;
         const __half* fb = sg.ptr + sl.choff + frame_in * pitch;
         const __half* fb_lo = kExact ? p.seg[sl.seg + kMaxSeg / 2].ptr + sl.choff + frame_in * pitch : nullptr;
-        for (int i = i_lo; i < i_hi; ++i) {
+        // ---- item loaders / consumers (forced inline; the item loop is fully unrolled so that everything
+        // stays in registers).  In fp16 mode the loads of item i+1 are issued before item i is blended
+        // (software pipelining: global latency ~1k cycles per item with only 2 producer warps per scheduler).
+        auto load_item = [&](int i, uint4 (&nb)[9], uint4 (&nbl)[9], float2 (&lyx)[8], int& oct) {
             const int r = prow + 32 * i;
             const int oy = ty0 + (r >> 4);
             const bool live = sl.valid && oy < p.Hout && ox < p.Wout;
-            // ---- stencil of this pixel: octant + (ly, lx) per rotated tap
-            float2 lyx[8];
-            int oct = 0;
+            oct = 0;
             if (live) {
                 const size_t e = static_cast<size_t>(oy) * p.Wout + ox;
                 const float4* tp = reinterpret_cast<const float4*>(p.ric_lyx + e * 8);
@@ -65,8 +67,6 @@ __device__ __forceinline__ void ric_produce(const ConvParams& p, uint8_t* a_smem
 #pragma unroll
                 for (int t = 0; t < 8; ++t) lyx[t] = make_float2(0.0f, 0.0f);
             }
-            // ---- 3x3 neighbourhood (virtual coordinates; the nearest-x2 upsample is the >> up)
-            uint4 nb[9], nbl[9];
 #pragma unroll
             for (int rr = 0; rr < 3; ++rr) {
                 const int vy = oy + rr - 1;
@@ -83,6 +83,9 @@ __device__ __forceinline__ void ric_produce(const ConvParams& p, uint8_t* a_smem
                     }
                 }
             }
+        };
+        auto blend_item = [&](int i, const uint4 (&nb)[9], const uint4 (&nbl)[9], const float2 (&lyx)[8], int oct) {
+            const int r = prow + 32 * i;
             // first item of a block: the previous block's MMAs must have drained the tap buffers
             if (b > 0 && i == i_lo) {
 #pragma unroll 1
@@ -92,7 +95,31 @@ __device__ __forceinline__ void ric_produce(const ConvParams& p, uint8_t* a_smem
             // ---- centre tap (raster tap 4): the pixel itself
             *reinterpret_cast<uint4*>(rowp + 4 * kABytes + slot_hi) = nb[4];
             if (kExact) *reinterpret_cast<uint4*>(rowp + 4 * kABytes + slot_lo) = nbl[4];
-            if constexpr (!kExact) {
+            if constexpr (!kExact && kHalfBlend) {
+                // ---- fp16 mode, packed math: the neighbours stay half2, the 4 bilinear weights of a tap are
+                // rounded to fp16 and the blend is 1 HMUL2 + 3 HFMA2 per channel pair (no unpack / repack).
+                // Costs ~1.5 fp16 ulp more rounding on the A operand than the fp32 blend below.
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    const float ly = lyx[m].x, lx = lyx[m].y;
+                    const float hy = 1.0f - ly, hx = 1.0f - lx;
+                    const __half2 w00 = __float2half2_rn(hy * hx), w01 = __float2half2_rn(hy * lx);
+                    const __half2 w10 = __float2half2_rn(ly * hx), w11 = __float2half2_rn(ly * lx);
+                    const int r0 = ric_r0(m), c0 = ric_c0(m);
+                    const __half2* n00 = reinterpret_cast<const __half2*>(&nb[r0 * 3 + c0]);
+                    const __half2* n01 = reinterpret_cast<const __half2*>(&nb[r0 * 3 + c0 + 1]);
+                    const __half2* n10 = reinterpret_cast<const __half2*>(&nb[(r0 + 1) * 3 + c0]);
+                    const __half2* n11 = reinterpret_cast<const __half2*>(&nb[(r0 + 1) * 3 + c0 + 1]);
+                    uint4 v;
+                    __half2* o = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        o[c] = __hfma2(w11, n11[c], __hfma2(w10, n10[c], __hfma2(w01, n01[c], __hmul2(w00, n00[c]))));
+                    const int kq = (m - oct) & 7;
+                    const int tap = kq + (kq >> 2);
+                    *reinterpret_cast<uint4*>(rowp + tap * kABytes + slot_hi) = v;
+                }
+            } else if constexpr (!kExact) {
                 // ---- all 8 channels at once: 72 fp32 neighbours in registers, weights computed once per tap
                 float nf[9][8];
 #pragma unroll
@@ -154,6 +181,27 @@ __device__ __forceinline__ void ric_produce(const ConvParams& p, uint8_t* a_smem
                     }
                 }
             }
+        };
+        if constexpr (kExact) {
+            for (int i = i_lo; i < i_hi; ++i) {
+                uint4 nb[9], nbl[9];
+                float2 lyx[8];
+                int oct;
+                load_item(i, nb, nbl, lyx, oct);
+                blend_item(i, nb, nbl, lyx, oct);
+            }
+        } else {
+            uint4 nbA[9], nbB[9], nbl[9];
+            float2 lyA[8], lyB[8];
+            int octA, octB;
+            load_item(0, nbA, nbl, lyA, octA);
+            load_item(1, nbB, nbl, lyB, octB);
+            blend_item(0, nbA, nbl, lyA, octA);
+            load_item(2, nbA, nbl, lyA, octA);
+            blend_item(1, nbB, nbl, lyB, octB);
+            load_item(3, nbB, nbl, lyB, octB);
+            blend_item(2, nbA, nbl, lyA, octA);
+            blend_item(3, nbB, nbl, lyB, octB);
         }
         fence_proxy_async_smem();
 #pragma unroll 1
