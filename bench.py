@@ -176,6 +176,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the single JSON line (NCCL_DEBUG=VERSION prints a banner)
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -257,7 +258,7 @@ def main():
 
     if rank == 0:
         n_batches = (F + args.batch - 1) // args.batch
-        launches = args.steps * n_batches * pipe.launches_per_batch(args.batch, S, S)
+        launches = world * args.steps * n_batches * pipe.launches_per_batch(args.batch, S, S)
         line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "fp16" if args.precision == "fp16" else "fp16x3", "data": "synthetic",

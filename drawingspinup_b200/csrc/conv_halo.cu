@@ -226,7 +226,7 @@ cudaError_t launch_conv_halo(const ConvParams& p, cudaStream_t stream) {
         if (e != cudaSuccess) return e;
         attr_set[dev] = true;
     }
-    if (p.sa < 2 || p.sa > kMaxHaloBufs || p.sb < 2 || p.sb > kMaxStagesB || p.ns < 1 || p.ks < 1 ||
+    if (p.sa < 1 || p.sa > kMaxHaloBufs || p.sb < 2 || p.sb > kMaxStagesB || p.ns < 1 || p.ks < 1 ||
         p.ns * p.ks > kIssuersHalo || p.sb / p.ks < 2 || p.stride != 1 || p.ns * p.ks * p.Cout > 512 || p.tmem_cols < p.ns * p.ks * p.Cout ||
         conv_halo_smem_bytes(p) > 227 * 1024 || p.nchunks != p.nblocks * p.ksize * p.ksize || p.ks > p.ksize * p.ksize)
         return cudaErrorInvalidConfiguration;

@@ -613,12 +613,14 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
             p.halo = 1; p.ksize = L.k; p.pad = L.pad;
             // candidates in order of measured preference (profiles/r01d sweep): wide CTAs for 3x3 (weight-tile reuse),
             // sub-tile x K-split for 7x7 (halo size); the first that fits TMEM and shared memory wins
-            static const int cand3[][2] = {{4, 1}, {2, 2}, {2, 1}, {1, 2}, {1, 1}};
-            static const int cand7[][2] = {{2, 2}, {2, 1}, {1, 2}, {1, 1}, {1, 1}};
-            const int (*cand)[2] = L.k == 3 ? cand3 : cand7;
-            int env_ns = 0, env_ks = 0;
+            // {sub-tiles, K-split issuers, halo buffers}
+            static const int cand3[][3] = {{4, 1, 2}, {2, 2, 2}, {2, 1, 2}, {1, 2, 2}, {1, 1, 2}};
+            static const int cand7[][3] = {{4, 1, 1}, {2, 2, 2}, {2, 1, 2}, {1, 2, 2}, {1, 1, 2}};
+            const int (*cand)[3] = L.k == 3 ? cand3 : cand7;
+            int env_ns = 0, env_ks = 0, env_na = 0;
             if (const char* ev = std::getenv("DSU_HALO_NS")) env_ns = std::max(1, std::min(4, std::atoi(ev)));
-            if (const char* ev = std::getenv("DSU_HALO_KS")) env_ks = std::max(1, std::min(8, std::atoi(ev)));
+            if (const char* ev = std::getenv("DSU_HALO_KS")) env_ks = std::max(1, std::min(4, std::atoi(ev)));
+            if (const char* ev = std::getenv("DSU_HALO_NA")) env_na = std::max(1, std::min(3, std::atoi(ev)));
             bool found = false;
             for (int ci = 0; ci < 5 && !found; ++ci) {
                 const int ns = env_ns ? env_ns : cand[ci][0], ks = env_ks ? env_ks : cand[ci][1];
@@ -627,12 +629,12 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
                 p.halo_w = 8 * ns + 2 * L.pad;
                 p.halo_rows = (16 + 2 * L.pad) * p.halo_w;
                 p.halo_bytes = (p.halo_rows * 128 + 1023) & ~1023;
-                p.sa = 2;
-                const int left = 227 * 1024 - 2 * p.halo_bytes - 8 * 1024;
-                p.sb = std::min(kMaxStagesB, left / p.b_bytes);
+                p.sa = env_na ? env_na : cand[ci][2];
+                const int left = 227 * 1024 - p.sa * p.halo_bytes - 8 * 1024;
+                p.sb = left < 0 ? 0 : std::min(kMaxStagesB, left / p.b_bytes);
                 if (const char* ev = std::getenv("DSU_HALO_SB")) p.sb = std::max(2, std::min(p.sb, std::atoi(ev)));
                 p.sb = (p.sb / ks) * ks;
-                found = p.sb / ks >= 2;
+                found = p.sb / ks >= 3 || (ci == 4 && p.sb / ks >= 2);
             }
             if (!found) return fail(DSU_E_INVALID, "halo convolution does not fit in shared memory: " + L.name);
             cols = 32;
