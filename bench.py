@@ -231,8 +231,15 @@ def main():
                                     "gflop": fl / 1e9})
         top = max(layer_table, key=lambda r: r["ms"])
         peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath) and args.batch == 16 and S == 512:
+            with open(tpath) as f:
+                ent = json.load(f).get(top["kernel"])
+            if ent:
+                traffic, traffic_src = ent["bytes"], ent["source"]
         roof = {"bound": "tensor", "kernel": top["kernel"], "achieved": top["tflops"], "peak": peak, "unit": "TFLOP/s",
-                "frac": top["tflops"] / peak, "traffic": None,
+                "frac": top["tflops"] / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % peak_kind,
                 "launch_ms": top["ms"], "launch_gflop": top["gflop"],
                 "whole_step_frac": (pipe.flops_per_frame(S, S) * fps / world / 1e12) / peak}
