@@ -101,18 +101,44 @@ class StylizationPipeline:
     @torch.no_grad()
     def run_host(self, color: torch.Tensor, pos: torch.Tensor, edge: torch.Tensor, out: torch.Tensor):
         """Same from / to HOST (pinned) uint8 stacks: per batch the inputs are copied to the device,
-        both stages run, and the stage-2 RGBA result is copied back (``out`` is filled in place)."""
+        both stages run, and the stage-2 RGBA result is copied back (``out`` is filled in place).
+        Copies run on a second stream so that the upload of batch i+1 and the download of batch i-1
+        overlap the kernels of batch i (frames are independent, so this is plain double buffering)."""
         n = color.shape[0]
-        st = torch.cuda.current_stream(self.device)
-        for lo in range(0, n, self.batch):
-            hi = min(n, lo + self.batch)
-            c = color[lo:hi].to(self.device, non_blocking=True)
-            p = pos[lo:hi].to(self.device, non_blocking=True)
-            e = edge[lo:hi].to(self.device, non_blocking=True)
+        main = torch.cuda.current_stream(self.device)
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(self.device)
+        cs = self._copy_stream
+        spans = [(lo, min(n, lo + self.batch)) for lo in range(0, n, self.batch)]
+
+        def upload(span):
+            lo, hi = span
+            with torch.cuda.stream(cs):
+                bufs = tuple(t[lo:hi].to(self.device, non_blocking=True) for t in (color, pos, edge))
+                ev = torch.cuda.Event()
+                ev.record(cs)
+            return bufs, ev
+
+        cs.wait_stream(main)
+        nxt = upload(spans[0]) if spans else None
+        pending = []
+        for i, (lo, hi) in enumerate(spans):
+            (c, p, e), ev = nxt
+            nxt = upload(spans[i + 1]) if i + 1 < len(spans) else None
+            main.wait_event(ev)
             r1 = self.g1.forward_frames(c, p, None)
             r2 = self.g2.forward_frames(r1, p, e)
-            out[lo:hi].copy_(r2, non_blocking=True)
-        st.synchronize()
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(cs):
+                cs.wait_event(done)
+                out[lo:hi].copy_(r2, non_blocking=True)
+            for t in (c, p, e):
+                t.record_stream(main)          # allocated on the copy stream, consumed by the kernels
+            r2.record_stream(cs)               # produced on the main stream, downloaded on the copy stream
+            pending.append((c, p, e, r1, r2))
+        cs.synchronize()
+        main.synchronize()
         return out
 
     def flops_per_frame(self, h: int, w: int) -> float:
