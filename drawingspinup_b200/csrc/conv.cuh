@@ -98,6 +98,7 @@ struct ConvParams {
     // order m = (octant + k) & 7, the bilinear fractions (ly, lx) relative to the static quadrant of m
     const float2* ric_lyx;  // [Hout*Wout][8]
     const uint8_t* ric_oct; // [Hout*Wout]
+    const uint2* ric_wh;    // [Hout*Wout][8] the 4 bilinear weights of each rotated tap as fp16 {w00,w01 | w10,w11} (packed-half2 blend)
     EpiParams epi;
 };
 

@@ -76,6 +76,7 @@ struct Level {
     int h = 0, w = 0;
     float2* lyx = nullptr;    // [h*w][8] bilinear fractions in rotated tap order
     uint8_t* oct = nullptr;   // [h*w] octant (tap rotation) of the pixel
+    uint2* wh = nullptr;      // [h*w][8] fp16 bilinear weights {w00,w01,w10,w11} per rotated tap
     float max_clamp = 0;      // largest adjustment needed to express a tap in its static quadrant
 };
 
@@ -446,6 +447,7 @@ int build_level(dsu_engine* E, Level& lv, int h, int w) {
     const size_t hw = static_cast<size_t>(h) * w;
     std::vector<float2> lyx(8 * hw);
     std::vector<uint8_t> oct(hw);
+    std::vector<uint2> wh(8 * hw);
     float worst = 0.0f;
     for (int y = 0; y < h; ++y)
         for (int x = 0; x < w; ++x) {
@@ -481,7 +483,13 @@ int build_level(dsu_engine* E, Level& lv, int h, int w) {
                 const int m = (best_o + kq) & 7;
                 const float ly = dyv[kq] - ((m >= 2 && m <= 5) ? -1.0f : 0.0f);
                 const float lx = dxv[kq] - ((m >= 4) ? -1.0f : 0.0f);
-                lyx[e * 8 + m] = make_float2(std::min(1.0f, std::max(0.0f, ly)), std::min(1.0f, std::max(0.0f, lx)));
+                const float cy = std::min(1.0f, std::max(0.0f, ly)), cxl = std::min(1.0f, std::max(0.0f, lx));
+                lyx[e * 8 + m] = make_float2(cy, cxl);
+                const float hy = 1.0f - cy, hx = 1.0f - cxl;
+                const __half w4[4] = {__float2half_rn(hy * hx), __float2half_rn(hy * cxl), __float2half_rn(cy * hx), __float2half_rn(cy * cxl)};
+                uint2 packed;
+                std::memcpy(&packed, w4, 8);
+                wh[e * 8 + m] = packed;
             }
         }
     if (worst > 1e-3f)
@@ -490,6 +498,7 @@ int build_level(dsu_engine* E, Level& lv, int h, int w) {
     int rc;
     if ((rc = upload(&lv.lyx, lyx))) return rc;
     if ((rc = upload(&lv.oct, oct))) return rc;
+    if ((rc = upload(&lv.wh, wh))) return rc;
     lv.h = h; lv.w = w; lv.max_clamp = worst;
     return DSU_OK;
 }
@@ -591,7 +600,7 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
             p.seg[i + kMaxSeg / 2].ptr = E->buf_lo[L.segs[i].buf];
             p.seg[i + kMaxSeg / 2].pitch = E->buf_C[L.segs[i].buf];
         }
-        if (L.ric) { p.ric_lyx = E->lv[L.level_out].lyx; p.ric_oct = E->lv[L.level_out].oct; }
+        if (L.ric) { p.ric_lyx = E->lv[L.level_out].lyx; p.ric_oct = E->lv[L.level_out].oct; p.ric_wh = E->lv[L.level_out].wh; }
         EpiParams& e = p.epi;
         e.scale = L.d_scale; e.shift = L.d_shift; e.scale2 = L.d_scale2; e.shift2 = L.d_shift2;
         e.act = L.act; e.resid_in = L.resid_in; e.resid_out = L.resid_out; e.resid = E->resid;
@@ -706,7 +715,7 @@ void dsu_destroy(dsu_handle h) {
         cudaFree(L.d_scale); cudaFree(L.d_shift); cudaFree(L.d_scale2); cudaFree(L.d_shift2);
     }
     for (int b = 0; b < NBUF; ++b) { cudaFree(h->buf_hi[b]); cudaFree(h->buf_lo[b]); }
-    for (int l = 0; l < 3; ++l) { cudaFree(h->lv[l].lyx); cudaFree(h->lv[l].oct); }
+    for (int l = 0; l < 3; ++l) { cudaFree(h->lv[l].lyx); cudaFree(h->lv[l].oct); cudaFree(h->lv[l].wh); }
     cudaFree(h->resid); cudaFree(h->d_w12); cudaFree(h->d_b12);
     cudaFree(h->io_color); cudaFree(h->io_pos); cudaFree(h->io_edge); cudaFree(h->io_out);
     delete h;

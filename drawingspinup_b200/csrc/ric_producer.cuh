@@ -55,7 +55,8 @@ __device__ __forceinline__ void ric_produce(const ConvParams& p, uint8_t* a_smem
             oct = 0;
             if (live) {
                 const size_t e = static_cast<size_t>(oy) * p.Wout + ox;
-                const float4* tp = reinterpret_cast<const float4*>(p.ric_lyx + e * 8);
+                const float4* tp = kHalfBlend ? reinterpret_cast<const float4*>(p.ric_wh + e * 8)      // fp16 weights, same 64 B / pixel
+                                              : reinterpret_cast<const float4*>(p.ric_lyx + e * 8);
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     const float4 v = __ldg(tp + t);
@@ -101,10 +102,9 @@ __device__ __forceinline__ void ric_produce(const ConvParams& p, uint8_t* a_smem
                 // Costs ~1.5 fp16 ulp more rounding on the A operand than the fp32 blend below.
 #pragma unroll
                 for (int m = 0; m < 8; ++m) {
-                    const float ly = lyx[m].x, lx = lyx[m].y;
-                    const float hy = 1.0f - ly, hx = 1.0f - lx;
-                    const __half2 w00 = __float2half2_rn(hy * hx), w01 = __float2half2_rn(hy * lx);
-                    const __half2 w10 = __float2half2_rn(ly * hx), w11 = __float2half2_rn(ly * lx);
+                    // table entry = {w00,w01 | w10,w11} in fp16 (host: fp32 products of (1-ly),(1-lx),ly,lx rounded once)
+                    const __half2 wa = *reinterpret_cast<const __half2*>(&lyx[m].x), wb = *reinterpret_cast<const __half2*>(&lyx[m].y);
+                    const __half2 w00 = __low2half2(wa), w01 = __high2half2(wa), w10 = __low2half2(wb), w11 = __high2half2(wb);
                     const int r0 = ric_r0(m), c0 = ric_c0(m);
                     const __half2* n00 = reinterpret_cast<const __half2*>(&nb[r0 * 3 + c0]);
                     const __half2* n01 = reinterpret_cast<const __half2*>(&nb[r0 * 3 + c0 + 1]);
