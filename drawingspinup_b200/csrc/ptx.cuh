@@ -116,6 +116,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
     d |= static_cast<uint64_t>(2) << 61;                 // SWIZZLE_128B
     return d;
 }
+// (probe only, tools/umma_probe64.cu - a double-buffered 32-channel RIC variant built on it measured 15 % slower
+// than the 64-channel single-set producer and was dropped)  Same for 64-byte rows (32 fp16 of K), SWIZZLE_64B: 16-byte chunk index XOR ((row >> 1) & 3) on absolute
+// address bits [4:5] ^= [7:8]; 8-row groups are `sbo_bytes` apart (512 when rows are contiguous).
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(4) << 61;                 // SWIZZLE_64B
+    return d;
+}
 // Instruction descriptor: fp16 A/B (K-major), fp32 D, M x N tile.
 __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t m, uint32_t n) {
     return (1u << 4) | ((n >> 3) << 17) | ((m >> 4) << 24);
