@@ -626,7 +626,8 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
             static const int cand3[][3] = {{4, 1, 2}, {2, 2, 2}, {2, 1, 2}, {1, 2, 2}, {1, 1, 2}};
             static const int cand7[][3] = {{4, 1, 1}, {2, 2, 2}, {2, 1, 2}, {1, 2, 2}, {1, 1, 2}};
             const int (*cand)[3] = L.k == 3 ? cand3 : cand7;
-            int env_ns = 0, env_ks = 0, env_na = 0;
+            int env_ns = 0, env_ks = 0, env_na = 0, persist_mode = 2;   // 0 never, 1 when the chosen config allows, 2 prefer (measured best)
+            if (const char* ev = std::getenv("DSU_HALO_PERSIST")) persist_mode = std::atoi(ev);
             if (const char* ev = std::getenv("DSU_HALO_NS")) env_ns = std::max(1, std::min(4, std::atoi(ev)));
             if (const char* ev = std::getenv("DSU_HALO_KS")) env_ks = std::max(1, std::min(4, std::atoi(ev)));
             if (const char* ev = std::getenv("DSU_HALO_NA")) env_na = std::max(1, std::min(3, std::atoi(ev)));
@@ -634,6 +635,7 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
             for (int ci = 0; ci < 5 && !found; ++ci) {
                 const int ns = env_ns ? env_ns : cand[ci][0], ks = env_ks ? env_ks : cand[ci][1];
                 if (ns * ks > kIssuersHalo || ns * ks * L.cout > 512 || ks > L.k * L.k) continue;
+                if (persist_mode == 2 && 2 * ns * ks * L.cout > 512) continue;     // only configurations that can double-buffer TMEM
                 p.ns = ns; p.ks = ks;
                 p.halo_w = 8 * ns + 2 * L.pad;
                 p.halo_rows = (16 + 2 * L.pad) * p.halo_w;
@@ -646,10 +648,13 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
                 found = p.sb / ks >= 3 || (ci == 4 && p.sb / ks >= 2);
             }
             if (!found) return fail(DSU_E_INVALID, "halo convolution does not fit in shared memory: " + L.name);
+            // persistent CTAs with double-buffered accumulators when two accumulator sets fit in TMEM
+            const bool persist = persist_mode != 0 && 2 * p.ns * p.ks * L.cout <= 512;
             cols = 32;
-            while (cols < p.ns * p.ks * L.cout) cols *= 2;
+            while (cols < (persist ? 2 : 1) * p.ns * p.ks * L.cout) cols *= 2;
             p.tmem_cols = cols;
-            CUDA_TRY(launch_conv_halo(p, st));
+            if (persist) CUDA_TRY(launch_conv_halo_persist(p, st));
+            else CUDA_TRY(launch_conv_halo(p, st));
         } else {
             CUDA_TRY(launch_conv(p, st));
         }
