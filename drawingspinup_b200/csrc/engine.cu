@@ -557,6 +557,8 @@ void pick_stages(bool ric, int b_bytes, int* sa, int* sb) {
 int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgba, const uint8_t* alpha_src,
                 int alpha_stride, cudaStream_t st, std::vector<cudaEvent_t>* evs = nullptr) {
     size_t step_idx = 0;
+    int ric_persist_mode = 1;     // 0 never, 1 Cout <= 64, 2 all RIC layers
+    if (const char* ev = std::getenv("DSU_RIC_PERSIST")) ric_persist_mode = std::atoi(ev);
     for (const Step& sp : E->steps) {
         if (evs) CUDA_TRY(cudaEventRecord((*evs)[step_idx], st));
         ++step_idx;
@@ -655,6 +657,14 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
             p.tmem_cols = cols;
             if (persist) CUDA_TRY(launch_conv_halo_persist(p, st));
             else CUDA_TRY(launch_conv_halo(p, st));
+        } else if (L.ric && ric_persist_mode != 0 && L.cout <= (ric_persist_mode == 2 ? 128 : 64)) {
+            // persistent CTAs, epilogue overlapped with the next tile (two accumulator sets in TMEM)
+            p.ks = std::max(1, std::min(p.ks, 256 / L.cout));
+            p.sb = (p.sb / p.ks) * p.ks;
+            cols = 32;
+            while (cols < 2 * p.ks * L.cout) cols *= 2;
+            p.tmem_cols = cols;
+            CUDA_TRY(launch_conv_ric_persist(p, st));
         } else {
             CUDA_TRY(launch_conv(p, st));
         }

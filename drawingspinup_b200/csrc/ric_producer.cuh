@@ -20,8 +20,9 @@ __device__ __forceinline__ constexpr int ric_c0(int m) { return (m >= 4) ? 0 : 1
 //                 four pixel rows, reads hi + lo planes and writes fp16 hi and lo = fp16(v - hi).
 // kHalfBlend (fp16 mode only): blend with packed half2 math instead of fp32.
 template <bool kExact, bool kHalfBlend>
+// g0 = number of blocks this CTA has already produced (persistent kernel: the tap-buffer barriers keep counting across tiles).
 __device__ __forceinline__ void ric_produce(const ConvParams& p, uint8_t* a_smem, uint32_t bar_full_a, uint32_t bar_empty_a,
-                                            int tid, int n, int ty0, int tx0) {
+                                            int tid, int n, int ty0, int tx0, int g0 = 0) {
     const int j = tid & 7, prow = tid >> 3, swz = prow & 7;
     const int cg = kExact ? (j & 3) : j;
     const int i_lo = kExact ? 2 * (j >> 2) : 0;
@@ -88,9 +89,9 @@ __device__ __forceinline__ void ric_produce(const ConvParams& p, uint8_t* a_smem
         auto blend_item = [&](int i, const uint4 (&nb)[9], const uint4 (&nbl)[9], const float2 (&lyx)[8], int oct) {
             const int r = prow + 32 * i;
             // first item of a block: the previous block's MMAs must have drained the tap buffers
-            if (b > 0 && i == i_lo) {
+            if (g0 + b > 0 && i == i_lo) {
 #pragma unroll 1
-                for (int t = 0; t < 9; ++t) mbar_wait(bar_empty_a + 8 * t, (b - 1) & 1);
+                for (int t = 0; t < 9; ++t) mbar_wait(bar_empty_a + 8 * t, (g0 + b - 1) & 1);
             }
             uint8_t* rowp = a_smem + r * 128;
             // ---- centre tap (raster tap 4): the pixel itself
