@@ -557,7 +557,7 @@ void pick_stages(bool ric, int b_bytes, int* sa, int* sb) {
 int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgba, const uint8_t* alpha_src,
                 int alpha_stride, cudaStream_t st, std::vector<cudaEvent_t>* evs = nullptr) {
     size_t step_idx = 0;
-    int ric_persist_mode = 1;     // 0 never, 1 Cout <= 64, 2 all RIC layers
+    int ric_persist_mode = 2;     // 0 never, 1 Cout <= 64, 2 all RIC layers (measured best: profiles/r01j)
     if (const char* ev = std::getenv("DSU_RIC_PERSIST")) ric_persist_mode = std::atoi(ev);
     for (const Step& sp : E->steps) {
         if (evs) CUDA_TRY(cudaEventRecord((*evs)[step_idx], st));
