@@ -90,6 +90,7 @@ struct ConvParams {
     // halo mode (plain stride-1 convs): one (16+2p) x (8*ns+2p) pixel halo tile per 64-channel block
     // is staged once and every tap reads a shifted window of it through the UMMA descriptor
     int halo, ns, ks, ksize, pad, halo_w, halo_rows, halo_bytes;   // ks: K-split issuers per sub-tile
+    int tps;                // persistent halo kernel: taps per weight stage (one bulk copy / one commit per tps taps)
     const Slot* slots;      // plain: [nchunks][8]; RIC: [nblocks][8]
     const ChunkHdr* hdrs;   // [nchunks]
     const uint8_t* wpack;   // pre-swizzled B tiles

@@ -41,7 +41,9 @@ conv_halo_persist_kernel(const __grid_constant__ ConvParams p) {
     const int NA = p.sa, SB = p.sb, C = p.Cout, NS = p.ns, KS = p.ks;
     const int NI = NS * KS;
     const int SBK = SB / KS;
-    const PersistSmem L = persist_smem(NA, p.halo_bytes, SB, p.b_bytes, C);
+    const int TPS = p.tps;                                   // taps per weight stage (> 1 only with ks == 1)
+    const int stage_bytes = TPS * p.b_bytes;
+    const PersistSmem L = persist_smem(NA, p.halo_bytes, SB, stage_bytes, C);
     float* s_par = reinterpret_cast<float*>(smem + L.par);
     const uint32_t bar_full_a = base + L.bars;
     const uint32_t bar_empty_a = bar_full_a + kMaxHaloBufs * 8;
@@ -164,35 +166,43 @@ conv_halo_persist_kernel(const __grid_constant__ ConvParams p) {
                     const uint32_t km2 = b == p.nblocks - 1 ? p.kmask2_last : p.kmask2_full;
                     mbar_wait(bar_full_a + 8 * s_a, (g / NA) & 1);
                     const uint32_t sub_addr = base + L.a0 + s_a * p.halo_bytes + static_cast<uint32_t>(sub) * 1024u;
-                    for (int t = ksp; t < taps; t += KS, ++cnt) {
+                    // a weight stage holds TPS consecutive taps (one wait + one commit per stage: the ~450-cycle commit
+                    // group cost measured in tools/umma_rate.cu is paid once per TPS taps)
+                    for (int t0 = ksp * TPS; t0 < taps; t0 += KS * TPS, ++cnt) {
                         const int s_b = ksp * SBK + cnt % SBK;
-                        const int kh = t / p.ksize, kw = t - kh * p.ksize;
+                        const int nt = (taps - t0) < TPS ? (taps - t0) : TPS;
                         mbar_wait(bar_full_b + 8 * s_b, (cnt / SBK) & 1);
                         tc_fence_after();
-                        const uint32_t b_addr = base + L.b0 + s_b * p.b_bytes;
-                        const uint32_t a_addr = sub_addr + static_cast<uint32_t>(kh * p.halo_w + kw) * 128u;
-                        if (elect_one()) {
-                            const uint64_t da0 = umma_desc_sw128(a_addr, sbo);
-                            const uint64_t db0 = umma_desc_sw128(b_addr, 1024);
-                            if (km == 0xFu) {
-                                umma_f16(d_addr, da0, db0, idesc, acc);
-                                umma_f16(d_addr, da0 + 2, db0 + 2, idesc, 1u);
-                                umma_f16(d_addr, da0 + 4, db0 + 4, idesc, 1u);
-                                umma_f16(d_addr, da0 + 6, db0 + 6, idesc, 1u);
-                            } else {
-                                uint32_t a2 = acc;
+                        for (int u = 0; u < nt; ++u) {           // warp-uniform address math, elected lane issues
+                            const int t = t0 + u;
+                            const int kh = t / p.ksize, kw = t - kh * p.ksize;
+                            const uint32_t b_addr = base + L.b0 + s_b * stage_bytes + u * p.b_bytes;
+                            const uint32_t a_addr = sub_addr + static_cast<uint32_t>(kh * p.halo_w + kw) * 128u;
+                            if (elect_one()) {
+                                const uint64_t da0 = umma_desc_sw128(a_addr, sbo);
+                                const uint64_t db0 = umma_desc_sw128(b_addr, 1024);
+                                if (km == 0xFu) {
+                                    umma_f16(d_addr, da0, db0, idesc, acc);
+                                    umma_f16(d_addr, da0 + 2, db0 + 2, idesc, 1u);
+                                    umma_f16(d_addr, da0 + 4, db0 + 4, idesc, 1u);
+                                    umma_f16(d_addr, da0 + 6, db0 + 6, idesc, 1u);
+                                } else {
+                                    uint32_t a2 = acc;
 #pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    if ((km >> k) & 1) { umma_f16(d_addr, da0 + 2 * k, db0 + 2 * k, idesc, a2); a2 = 1u; }
-                            }
-                            if (km2) {
-                                const uint64_t db1 = umma_desc_sw128(b_addr + C * 128, 1024);
+                                    for (int k = 0; k < 4; ++k)
+                                        if ((km >> k) & 1) { umma_f16(d_addr, da0 + 2 * k, db0 + 2 * k, idesc, a2); a2 = 1u; }
+                                }
+                                if (km2) {
+                                    const uint64_t db1 = umma_desc_sw128(b_addr + C * 128, 1024);
 #pragma unroll
-                                for (int k = 0; k < 2; ++k)
-                                    if ((km2 >> k) & 1) umma_f16(d_addr, da0 + 2 * k, db1 + 2 * k, idesc, 1u);
+                                    for (int k = 0; k < 2; ++k)
+                                        if ((km2 >> k) & 1) umma_f16(d_addr, da0 + 2 * k, db1 + 2 * k, idesc, 1u);
+                                }
                             }
-                            umma_commit(bar_empty_b + 8 * s_b);
+                            acc = 1u;
+                            __syncwarp();
                         }
+                        if (elect_one()) umma_commit(bar_empty_b + 8 * s_b);   // same elected lane as the MMAs it tracks
                         acc = 1u;
                         __syncwarp();
                     }
@@ -210,17 +220,18 @@ conv_halo_persist_kernel(const __grid_constant__ ConvParams p) {
         int cnt[kIssuersHalo] = {0, 0, 0, 0};
         for (int it = 0; it < my_tiles; ++it)
             for (int b = 0; b < p.nblocks; ++b)
-                for (int t = 0; t < taps; ++t) {
-                    const int k = t % KS;
+                for (int t0 = 0, grp = 0; t0 < taps; t0 += TPS, ++grp) {
+                    const int k = grp % KS;
+                    const int nt = (taps - t0) < TPS ? (taps - t0) : TPS;
                     int c = 0;
 #pragma unroll
                     for (int i = 0; i < kIssuersHalo; ++i) if (i == k) { c = cnt[i]; cnt[i] = c + 1; }
                     const int s = k * SBK + c % SBK;
                     if (c >= SBK) mbar_wait(bar_empty_b + 8 * s, ((c / SBK) - 1) & 1);
                     if (elect_one()) {
-                        mbar_arrive_expect_tx(bar_full_b + 8 * s, static_cast<uint32_t>(p.b_bytes));
-                        bulk_g2s(base + L.b0 + s * p.b_bytes, p.wpack + static_cast<size_t>(b * taps + t) * p.b_bytes,
-                                 static_cast<uint32_t>(p.b_bytes), bar_full_b + 8 * s);
+                        const uint32_t bytes = static_cast<uint32_t>(nt * p.b_bytes);
+                        mbar_arrive_expect_tx(bar_full_b + 8 * s, bytes);
+                        bulk_g2s(base + L.b0 + s * stage_bytes, p.wpack + static_cast<size_t>(b * taps + t0) * p.b_bytes, bytes, bar_full_b + 8 * s);
                     }
                     __syncwarp();
                 }
@@ -234,7 +245,7 @@ conv_halo_persist_kernel(const __grid_constant__ ConvParams p) {
 }
 
 size_t conv_halo_persist_smem_bytes(const ConvParams& p) {
-    return persist_smem(p.sa, p.halo_bytes, p.sb, p.b_bytes, p.Cout).total + 1024;
+    return persist_smem(p.sa, p.halo_bytes, p.sb, p.tps * p.b_bytes, p.Cout).total + 1024;
 }
 
 cudaError_t launch_conv_halo_persist(const ConvParams& p, cudaStream_t stream) {
@@ -250,7 +261,7 @@ cudaError_t launch_conv_halo_persist(const ConvParams& p, cudaStream_t stream) {
         attr_set[dev] = true;
     }
     if (p.sa < 1 || p.sa > kMaxHaloBufs || p.sb < 2 || p.sb > kMaxStagesB || p.ns < 1 || p.ks < 1 ||
-        p.ns * p.ks > kIssuersHalo || p.sb / p.ks < 2 || p.stride != 1 || 2 * p.ns * p.ks * p.Cout > 512 ||
+        p.ns * p.ks > kIssuersHalo || p.sb / p.ks < 2 || p.stride != 1 || 2 * p.ns * p.ks * p.Cout > 512 || p.tps < 1 || p.tps > 4 ||
         p.tmem_cols < 2 * p.ns * p.ks * p.Cout || conv_halo_persist_smem_bytes(p) > 227 * 1024 ||
         p.nchunks != p.nblocks * p.ksize * p.ksize || p.ks > p.ksize * p.ksize)
         return cudaErrorInvalidConfiguration;
