@@ -165,6 +165,12 @@ def main():
         return 0
     args.warmup = max(args.warmup, 3)
 
+    # stdout must carry exactly ONE JSON line: route everything printed before it (e.g. the NCCL version banner
+    # written from C) to stderr and restore the real stdout just for the result line.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -277,7 +283,10 @@ def main():
                         "d2h_bytes_per_step": int(world * F * S * S * 4), "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base,
                 "parity_grade": exact, "layers": layer_table}
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
     return 0
