@@ -297,10 +297,13 @@ int compile_layer(dsu_engine* E, LayerDef& L) {
             else slots.push_back(Slot{});
         }
     };
+    // halo-reuse kernel: plain stride-1 convs with >= 32 channels per tap (the 8-channel 7x7 conv0 was measured slower
+    // there: 49 single-K-step MMAs per tile; it stays in tap mode where 8 taps share one 64-element chunk)
     L.halo = (!L.ric && !L.expanded && L.stride == 1 && real_k / (k * k) >= 32) ? 1 : 0;
     if (L.expanded) {
-        // data slot = (tap, 8-channel group) of the expanded buffer [pix][tap * nch + c]; weights keep their 3x3 index
-        L.halo = 0;
+        // data slot = (tap, 8-channel group) of the expanded buffer [pix][tap * nch + c]; weights keep their 3x3 index.
+        // Runs in the halo kernel as a 1x1 convolution: blocks of 8 data slots, one "tap" (chunk) per block.
+        L.halo = 1;
         const SegDef& s0 = L.segs[0];
         std::vector<HSlot> all;
         for (int tap = 0; tap < k * k; ++tap)
@@ -311,7 +314,7 @@ int compile_layer(dsu_engine* E, LayerDef& L) {
             push_dev_slots(ds);
             chunks.push_back(ds);
         }
-        L.nblocks = 0;
+        L.nblocks = static_cast<int>(chunks.size());
     } else if (!L.ric && !L.halo) {
         std::vector<HSlot> all;
         for (int kh = 0; kh < k; ++kh)
@@ -621,13 +624,14 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
         if (L.halo) {
             // ns sub-tiles x ks K-split issuers (<= 4 issuing warps, <= 512 TMEM columns); shared memory:
             // 2 halo buffers + as many weight stages as fit
-            p.halo = 1; p.ksize = L.k; p.pad = L.pad;
+            const int kk = L.expanded ? 1 : L.k, pp = L.expanded ? 0 : L.pad;     // expanded conv0 = 1x1 over the tap-expanded buffer
+            p.halo = 1; p.ksize = kk; p.pad = pp;
             // candidates in order of measured preference (profiles/r01d sweep): wide CTAs for 3x3 (weight-tile reuse),
             // sub-tile x K-split for 7x7 (halo size); the first that fits TMEM and shared memory wins
             // {sub-tiles, K-split issuers, halo buffers}
             static const int cand3[][3] = {{4, 1, 2}, {2, 2, 2}, {2, 1, 2}, {1, 2, 2}, {1, 1, 2}};
             static const int cand7[][3] = {{4, 1, 1}, {2, 2, 2}, {2, 1, 2}, {1, 2, 2}, {1, 1, 2}};
-            const int (*cand)[3] = L.k == 3 ? cand3 : cand7;
+            const int (*cand)[3] = kk <= 3 ? cand3 : cand7;
             int env_ns = 0, env_ks = 0, env_na = 0, persist_mode = 2;   // 0 never, 1 when the chosen config allows, 2 prefer (measured best)
             if (const char* ev = std::getenv("DSU_HALO_PERSIST")) persist_mode = std::atoi(ev);
             if (const char* ev = std::getenv("DSU_HALO_NS")) env_ns = std::max(1, std::min(4, std::atoi(ev)));
@@ -636,11 +640,11 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
             bool found = false;
             for (int ci = 0; ci < 5 && !found; ++ci) {
                 const int ns = env_ns ? env_ns : cand[ci][0], ks = env_ks ? env_ks : cand[ci][1];
-                if (ns * ks > kIssuersHalo || ns * ks * L.cout > 512 || ks > L.k * L.k) continue;
+                if (ns * ks > kIssuersHalo || ns * ks * L.cout > 512 || ks > kk * kk) continue;
                 if (persist_mode == 2 && 2 * ns * ks * L.cout > 512) continue;     // only configurations that can double-buffer TMEM
                 p.ns = ns; p.ks = ks;
-                p.halo_w = 8 * ns + 2 * L.pad;
-                p.halo_rows = (16 + 2 * L.pad) * p.halo_w;
+                p.halo_w = 8 * ns + 2 * pp;
+                p.halo_rows = (16 + 2 * pp) * p.halo_w;
                 p.halo_bytes = (p.halo_rows * 128 + 1023) & ~1023;
                 p.sa = env_na ? env_na : cand[ci][2];
                 const int left = 227 * 1024 - p.sa * p.halo_bytes - 8 * 1024;
