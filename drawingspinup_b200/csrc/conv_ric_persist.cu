@@ -68,7 +68,7 @@ conv_ric_persist_kernel(const __grid_constant__ ConvParams p) {
     if (warp == 12) {
         if (lane == 0) {
             for (int s = 0; s < 9; ++s) {
-                mbar_init(bar_full_a + 8 * s, kWorkers);
+                mbar_init(bar_full_a + 8 * s, kWorkers / 32);     // one arrival per producer warp
                 mbar_init(bar_empty_a + 8 * s, 1);
             }
             for (int s = 0; s < SB; ++s) {

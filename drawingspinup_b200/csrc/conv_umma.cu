@@ -78,7 +78,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
     if (warp == 8) {
         if (lane == 0) {
             for (int s = 0; s < SA; ++s) {
-                mbar_init(bar_full_a + 8 * s, kWorkers);
+                mbar_init(bar_full_a + 8 * s, kRic ? kWorkers / 32 : kWorkers);   // RIC producers arrive once per warp
                 mbar_init(bar_empty_a + 8 * s, 1);
             }
             for (int s = 0; s < SB; ++s) {

@@ -89,9 +89,12 @@ __device__ __forceinline__ void ric_produce(const ConvParams& p, uint8_t* a_smem
         auto blend_item = [&](int i, const uint4 (&nb)[9], const uint4 (&nbl)[9], const float2 (&lyx)[8], int oct) {
             const int r = prow + 32 * i;
             // first item of a block: the previous block's MMAs must have drained the tap buffers
-            if (g0 + b > 0 && i == i_lo) {
+            if (g0 + b > 0 && i == i_lo) {      // one lane polls the 9 barriers, __syncwarp publishes the acquire to the warp
+                if ((tid & 31) == 0) {
 #pragma unroll 1
-                for (int t = 0; t < 9; ++t) mbar_wait(bar_empty_a + 8 * t, (g0 + b - 1) & 1);
+                    for (int t = 0; t < 9; ++t) mbar_wait(bar_empty_a + 8 * t, (g0 + b - 1) & 1);
+                }
+                __syncwarp();
             }
             uint8_t* rowp = a_smem + r * 128;
             // ---- centre tap (raster tap 4): the pixel itself
@@ -204,9 +207,13 @@ __device__ __forceinline__ void ric_produce(const ConvParams& p, uint8_t* a_smem
             blend_item(2, nbA, nbl, lyA, octA);
             blend_item(3, nbB, nbl, lyB, octB);
         }
+        // every lane fences its own smem writes, then one arrival per warp and tap (barrier count = 8 producer warps)
         fence_proxy_async_smem();
+        __syncwarp();
+        if ((tid & 31) == 0) {
 #pragma unroll 1
-        for (int t = 0; t < 9; ++t) mbar_arrive(bar_full_a + 8 * t);
+            for (int t = 0; t < 9; ++t) mbar_arrive(bar_full_a + 8 * t);
+        }
     }
 }
 

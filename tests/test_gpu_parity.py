@@ -310,6 +310,21 @@ def test_flop_model_and_launch_count(dev):
     assert m1.kernel_launches(1, 512, 512) == 1 + 21 + 3 and m2.kernel_launches(1, 512, 512) == 1 + 22
 
 
+def test_profile_hook_reports_every_launch(dev):
+    """dsu_profile_forward / dsu_step_name: one entry per launch after the ingest, FLOPs add up to the model's."""
+    for stage in (1, 2):
+        m, _ = _model(stage, dev, precision="fp16")
+        x = _frames_tensor(1, 64, 64, seed=4, stage=stage).to(dev)
+        with torch.no_grad():
+            m(x)
+        rows = m.profile_layers(1, 64, 64, reps=1)
+        assert len(rows) == m.kernel_launches(1, 64, 64) - 1
+        names = [r[0] for r in rows]
+        assert names[-1] == "conv_11_a.3" and "upconv1" in names and ("ric_expand" in names) == (stage == 1)
+        assert all(ms > 0 for _, ms, _ in rows)
+        assert abs(sum(f for _, _, f in rows) - m.algorithmic_flops(1, 64, 64)) / m.algorithmic_flops(1, 64, 64) < 1e-6
+
+
 def test_multi_gpu_shard_equivalence(dev):
     """N-GPU frame sharding == single GPU, bitwise."""
     if torch.cuda.device_count() < 2:
