@@ -37,7 +37,8 @@ struct Slot {
 };
 static_assert(sizeof(Slot) == 8, "Slot must be 8 bytes");
 
-// One K chunk (8 slots = 64 K elements) of the implicit GEMM.
+// Host-side description of one K chunk (8 slots = 64 K elements) of the implicit GEMM; the kernels get the masks as
+// launch constants (kmask_full / kmask_last) and the tile offset as chunk_index * b_bytes.
 struct ChunkHdr {
     uint8_t kmask;      // which of the 4 UMMA K=16 steps are issued against B tile 0
     uint8_t kmask2;     // exact mode: which of steps 0-1 (the hi half) are issued against B tile 1 (W_lo)
@@ -92,7 +93,6 @@ struct ConvParams {
     int halo, ns, ks, ksize, pad, halo_w, halo_rows, halo_bytes;   // ks: K-split issuers per sub-tile
     int tps;                // persistent halo kernel: taps per weight stage (one bulk copy / one commit per tps taps)
     const Slot* slots;      // plain: [nchunks][8]; RIC: [nblocks][8]
-    const ChunkHdr* hdrs;   // [nchunks]
     const uint8_t* wpack;   // pre-swizzled B tiles
     Seg seg[kMaxSeg];
     // RIC stencil of the output level, per pixel: octant (tap rotation) and, in rotated tap

@@ -30,7 +30,7 @@ namespace {
 constexpr int kNumBars = 2 * kMaxStagesA + 2 * kMaxStagesB + 1;
 
 struct SmemLayout {
-    uint32_t a0, b0, par, hdr, bars;   // byte offsets from the 1024-aligned base
+    uint32_t a0, b0, par, bars;   // byte offsets from the 1024-aligned base
     uint32_t total;
 };
 
@@ -39,8 +39,8 @@ __host__ __device__ inline SmemLayout smem_layout(int sa, int sb, int b_bytes, i
     L.a0 = 0;
     L.b0 = L.a0 + sa * kABytes;
     L.par = L.b0 + sb * b_bytes;
-    L.hdr = (L.par + (7 * cout + 4) * 4 + 15u) & ~15u;
-    L.bars = (L.hdr + nchunks * 8 + 15u) & ~15u;
+    (void)nchunks;
+    L.bars = (L.par + (7 * cout + 4) * 4 + 15u) & ~15u;
     L.total = L.bars + (kNumBars + 1) * 8;
     return L;
 }

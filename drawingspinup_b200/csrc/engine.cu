@@ -60,7 +60,6 @@ struct LayerDef {
     int nchunks = 0, nblocks = 0;
     uint32_t kmask_full = 0xF, kmask_last = 0xF, kmask2_full = 0, kmask2_last = 0;
     Slot* d_slots = nullptr;
-    ChunkHdr* d_hdrs = nullptr;
     uint8_t* d_wpack = nullptr;
     float *d_scale = nullptr, *d_shift = nullptr, *d_scale2 = nullptr, *d_shift2 = nullptr;
     double macs_per_px = 0;   // live MACs per output pixel
@@ -387,7 +386,6 @@ int compile_layer(dsu_engine* E, LayerDef& L) {
     L.kmask_last = hdrs.back().kmask; L.kmask2_last = hdrs.back().kmask2;
     int rc;
     if ((rc = upload(&L.d_slots, slots))) return rc;
-    if ((rc = upload(&L.d_hdrs, hdrs))) return rc;
     if ((rc = upload(&L.d_wpack, pack))) return rc;
 
     // epilogue affine: y = act(acc * scale + shift) [* scale2 + shift2]
@@ -598,7 +596,7 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
         int cols = 32;
         while (cols < p.ks * L.cout) cols *= 2;
         p.tmem_cols = cols;
-        p.slots = L.d_slots; p.hdrs = L.d_hdrs; p.wpack = L.d_wpack;
+        p.slots = L.d_slots; p.wpack = L.d_wpack;
         for (size_t i = 0; i < L.segs.size(); ++i) {
             p.seg[i].ptr = E->buf_hi[L.segs[i].buf];
             p.seg[i].pitch = E->buf_C[L.segs[i].buf];
@@ -740,7 +738,7 @@ void dsu_destroy(dsu_handle h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     for (LayerDef& L : h->layers) {
-        cudaFree(L.d_slots); cudaFree(L.d_hdrs); cudaFree(L.d_wpack);
+        cudaFree(L.d_slots); cudaFree(L.d_wpack);
         cudaFree(L.d_scale); cudaFree(L.d_shift); cudaFree(L.d_scale2); cudaFree(L.d_shift2);
     }
     for (int b = 0; b < NBUF; ++b) { cudaFree(h->buf_hi[b]); cudaFree(h->buf_lo[b]); }
