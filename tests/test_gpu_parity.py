@@ -56,7 +56,7 @@ def _frames_tensor(b, h, w, seed, stage):
 
 # ------------------------------------------------------------------ whole-network parity
 @pytest.mark.parametrize("stage", [1, 2])
-@pytest.mark.parametrize("shape", [(2, 64, 48), (1, 72, 100), (3, 32, 32)])
+@pytest.mark.parametrize("shape", [(2, 64, 48), (1, 72, 100), (3, 32, 32), (1, 4, 4), (2, 8, 12), (5, 20, 36)])
 def test_forward_matches_oracle_fp16x3(dev, stage, shape):
     b, h, w = shape
     m, sd = _model(stage, dev)
