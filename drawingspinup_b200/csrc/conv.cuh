@@ -41,7 +41,7 @@ static_assert(sizeof(Slot) == 8, "Slot must be 8 bytes");
 // launch constants (kmask_full / kmask_last) and the tile offset as chunk_index * b_bytes.
 struct ChunkHdr {
     uint8_t kmask;      // which of the 4 UMMA K=16 steps are issued against B tile 0
-    uint8_t kmask2;     // exact mode: which of steps 0-1 (the hi half) are issued against B tile 1 (W_lo)
+    uint8_t kmask2;     // exact mode: which of A steps 0-1 (the hi half) are issued against B steps 2-3 (W_lo)
     uint16_t pad_;
     uint32_t b_off;     // byte offset of this chunk's B tile(s) inside wpack
 };

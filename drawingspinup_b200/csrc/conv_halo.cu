@@ -156,7 +156,16 @@ conv_halo_kernel(const __grid_constant__ ConvParams p) {
                         // descriptors are built once per tap; a K=16 step advances the start-address field by 32 B (= 2)
                         const uint64_t da0 = umma_desc_sw128(a_addr, sbo);
                         const uint64_t db0 = umma_desc_sw128(b_addr, 1024);
-                        if (km == 0xFu) {
+                        if (km2) {
+                            // split-fp16: A = [a_hi | a_lo] (steps 0-1 | 2-3), B = [W_hi | W_lo]; a_hi*W_hi + a_lo*W_hi + a_hi*W_lo
+                            uint32_t a2 = acc;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if ((km >> k) & 1) { umma_f16(d_addr, da0 + 2 * k, db0 + 2 * (k & 1), idesc, a2); a2 = 1u; }
+#pragma unroll
+                            for (int k = 0; k < 2; ++k)
+                                if ((km2 >> k) & 1) umma_f16(d_addr, da0 + 2 * k, db0 + 4 + 2 * k, idesc, 1u);
+                        } else if (km == 0xFu) {
                             umma_f16(d_addr, da0, db0, idesc, acc);
                             umma_f16(d_addr, da0 + 2, db0 + 2, idesc, 1u);
                             umma_f16(d_addr, da0 + 4, db0 + 4, idesc, 1u);
@@ -166,12 +175,6 @@ conv_halo_kernel(const __grid_constant__ ConvParams p) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
                                 if ((km >> k) & 1) { umma_f16(d_addr, da0 + 2 * k, db0 + 2 * k, idesc, a2); a2 = 1u; }
-                        }
-                        if (km2) {
-                            const uint64_t db1 = umma_desc_sw128(b_addr + C * 128, 1024);
-#pragma unroll
-                            for (int k = 0; k < 2; ++k)
-                                if ((km2 >> k) & 1) umma_f16(d_addr, da0 + 2 * k, db1 + 2 * k, idesc, 1u);
                         }
                         umma_commit(bar_empty_b + 8 * s_b);
                     }

@@ -350,7 +350,7 @@ int compile_layer(dsu_engine* E, LayerDef& L) {
     L.nchunks = static_cast<int>(chunks.size());
     std::vector<ChunkHdr> hdrs(L.nchunks);
     const size_t tile = static_cast<size_t>(C) * 128;
-    std::vector<uint8_t> pack(static_cast<size_t>(L.nchunks) * tile * (exact ? 2 : 1), 0);
+    std::vector<uint8_t> pack(static_cast<size_t>(L.nchunks) * tile, 0);
     size_t off = 0;
     auto put = [&](size_t tile_off, int row, int slot, int ci, __half val) {
         const size_t b = tile_off + static_cast<size_t>(row) * 128 + ((static_cast<size_t>(slot) ^ (row & 7)) << 4) + ci * 2;
@@ -373,13 +373,10 @@ int compile_layer(dsu_engine* E, LayerDef& L) {
                     const float wv = Wt[((static_cast<size_t>(o) * cin_total + h.wch + ci) * k + h.kh) * k + h.kw];
                     const __half wh = __float2half_rn(wv);
                     put(off, o, d, ci, wh);
-                    if (exact) {
-                        put(off, o, d + 4, ci, wh);                                            // x a_lo
-                        put(off + tile, o, d, ci, __float2half_rn(wv - __half2float(wh)));     // W_lo x a_hi
-                    }
+                    if (exact) put(off, o, d + 4, ci, __float2half_rn(wv - __half2float(wh)));   // [W_hi | W_lo] in one row
                 }
             }
-        off += tile * (exact ? 2 : 1);
+        off += tile;
     }
     pack.resize(off);
     L.kmask_full = hdrs.front().kmask; L.kmask2_full = hdrs.front().kmask2;
@@ -584,7 +581,7 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
         // fp16 mode blends the RIC taps with packed half2 math unless DSU_RIC_FP32_BLEND=1 (p.ric == 2 selects it)
         if (L.ric && !E->exact && !std::getenv("DSU_RIC_FP32_BLEND")) p.ric = 2;
         p.nchunks = L.nchunks; p.nblocks = L.nblocks; p.Cout = L.cout;
-        p.b_bytes = (E->exact ? 2 : 1) * L.cout * 128;
+        p.b_bytes = L.cout * 128;
         p.kmask_full = L.kmask_full; p.kmask_last = L.kmask_last; p.kmask2_full = L.kmask2_full; p.kmask2_last = L.kmask2_last;
         pick_stages(L.ric != 0, p.b_bytes, &p.sa, &p.sb);
         p.ks = 1;
