@@ -50,12 +50,114 @@ __device__ __forceinline__ void load_epilogue_params(const ConvParams& p, float*
     if (p.epi.w12 && tid < 3) s_par[7 * C + tid] = p.epi.b12[tid];
 }
 
+// 8 fp32 -> packed fp16 (hi plane only)
+__device__ __forceinline__ uint4 pack8(const float* f) {
+    return make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
+}
+
+// 32 channels of one pixel -> fp16 NHWC (hi plane, plus the split-fp16 lo plane when kLo and `lo` is non-null)
+template <bool kLo>
+__device__ __forceinline__ void store32(__half* hi, __half* lo, const float* f) {
+    uint4* o = reinterpret_cast<uint4*>(hi);
+    if (kLo && lo) {
+        uint4* ol = reinterpret_cast<uint4*>(lo);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint4 h, l;
+            split8(f + 8 * c, h, l);
+            o[c] = h;
+            ol[c] = l;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) o[c] = pack8(f + 8 * c);
+    }
+}
+
+// One 32-column batch of one accumulator row after the K-split partial sums were added: folded BN / bias, activation,
+// optional post-activation affine, residual stream, fp16 stores, conv_12 partial dot products.  The activation, the
+// second affine and the lo plane are compile-time (dispatched once per row in epilogue_row): with run-time tests inside
+// the 32-element loops a batch cost ~210 instructions (113 of them branches) on a latency-bound lone warp
+// (profiles/r01m_conv_first.ncu-rep), this form ~70 + the stores.
+template <int kAct, int kScale2, bool kLo>   // kAct / kScale2 = -1: decided at run time (cold generic variant)
+__device__ __forceinline__ void epilogue_batch(const ConvParams& p, const float* s_par, const uint32_t* v, size_t opix, int cb,
+                                               bool tail, float* y3) {
+    const EpiParams& e = p.epi;
+    const int C = p.Cout;
+    float f[32];
+    {
+        const float4* sc = reinterpret_cast<const float4*>(s_par + cb);
+        const float4* sh = reinterpret_cast<const float4*>(s_par + C + cb);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 a = sc[q], b = sh[q];
+            f[4 * q] = fmaf(__uint_as_float(v[4 * q]), a.x, b.x);
+            f[4 * q + 1] = fmaf(__uint_as_float(v[4 * q + 1]), a.y, b.y);
+            f[4 * q + 2] = fmaf(__uint_as_float(v[4 * q + 2]), a.z, b.z);
+            f[4 * q + 3] = fmaf(__uint_as_float(v[4 * q + 3]), a.w, b.w);
+        }
+    }
+    const int act = kAct >= 0 ? kAct : e.act;
+    if (act == 1) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) f[c] = fmaxf(f[c], 0.0f);
+    } else if (act == 2) {           // LeakyReLU(0.2): max(x, 0.2 x) == (x > 0 ? x : 0.2 x) for every input
+#pragma unroll
+        for (int c = 0; c < 32; ++c) f[c] = fmaxf(f[c], 0.2f * f[c]);
+    }
+    if (kScale2 > 0 || (kScale2 < 0 && e.scale2)) {
+        const float4* sc = reinterpret_cast<const float4*>(s_par + 2 * C + cb);
+        const float4* sh = reinterpret_cast<const float4*>(s_par + 3 * C + cb);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 a = sc[q], b = sh[q];
+            f[4 * q] = fmaf(f[4 * q], a.x, b.x);
+            f[4 * q + 1] = fmaf(f[4 * q + 1], a.y, b.y);
+            f[4 * q + 2] = fmaf(f[4 * q + 2], a.z, b.z);
+            f[4 * q + 3] = fmaf(f[4 * q + 3], a.w, b.w);
+        }
+    }
+    if (e.resid_in) {
+        const float4* rp = reinterpret_cast<const float4*>(e.resid + opix * C + cb);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float4 rv = rp[c];
+            f[4 * c] += rv.x; f[4 * c + 1] += rv.y; f[4 * c + 2] += rv.z; f[4 * c + 3] += rv.w;
+        }
+    }
+    if (e.resid_out) {
+        float4* rp = reinterpret_cast<float4*>(e.resid + opix * C + cb);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) rp[c] = make_float4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]);
+    }
+    if (e.out2_hi)
+        store32<kLo>(e.out2_hi + opix * e.out2_pitch + e.out2_choff + cb,
+                     e.out2_lo ? e.out2_lo + opix * e.out2_pitch + e.out2_choff + cb : nullptr, f);
+    if (e.out_relu) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) f[c] = fmaxf(f[c], 0.0f);
+    }
+    if (e.out_hi)
+        store32<kLo>(e.out_hi + opix * e.out_pitch + e.out_choff + cb,
+                     e.out_lo ? e.out_lo + opix * e.out_pitch + e.out_choff + cb : nullptr, f);
+    if (tail) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            y3[0] = fmaf(f[c], s_par[4 * C + cb + c], y3[0]);
+            y3[1] = fmaf(f[c], s_par[5 * C + cb + c], y3[1]);
+            y3[2] = fmaf(f[c], s_par[6 * C + cb + c], y3[2]);
+        }
+    }
+}
+
 // One accumulator row (= one output pixel, all Cout columns) per thread.  `t_addr` = TMEM address of
 // this warp's lane quadrant at the accumulator's first column.  The two warps that share a lane
 // quadrant (chalf 0/1) split the 32-column batches; the conv_12 tail needs a whole row in one
 // thread, so only chalf 0 runs it.  Must be called by all 32 lanes of the warp (tcgen05.ld is
 // warp-collective); chalf is warp-uniform.
 // `nsplit` partial accumulators `split_stride` columns apart (K-split issuers) are summed first.
+constexpr uint32_t kEpiAll = 0xFFFFu, kEpiFp16 = 0x0027u, kEpiSplit = 0x2700u;   // variant masks (bit = variant index)
+template <uint32_t kMask = kEpiAll>
 __device__ __forceinline__ void epilogue_row(const ConvParams& p, const float* s_par, uint32_t t_addr,
                                              int n, int oy, int ox, int chalf, int nsplit = 1, int split_stride = 0, int csplit = 2) {
     const EpiParams& e = p.epi;
@@ -67,6 +169,8 @@ __device__ __forceinline__ void epilogue_row(const ConvParams& p, const float* s
     const int cb_first = tail ? 0 : chalf, cb_step = tail ? 1 : csplit;   // csplit warps share a lane quadrant
     const bool active = tail ? (chalf == 0) : (chalf < ncb);
     if (!active) return;
+    // warp-uniform variant index: activation | second affine | lo plane
+    const int variant = e.act | (e.scale2 ? 4 : 0) | ((e.out_lo || e.out2_lo) ? 8 : 0);
     float y3[3] = {0.0f, 0.0f, 0.0f};
     for (int cbi = cb_first; cbi < ncb; cbi += cb_step) {
         const int cb = cbi * 32;
@@ -81,62 +185,24 @@ __device__ __forceinline__ void epilogue_row(const ConvParams& p, const float* s
             for (int c = 0; c < 32; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(u[c]));
         }
         if (!pix_ok) continue;
-        float f[32];
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            float x = fmaf(__uint_as_float(v[c]), s_par[cb + c], s_par[C + cb + c]);
-            if (e.act == 1) x = fmaxf(x, 0.0f);
-            else if (e.act == 2) x = x > 0.0f ? x : 0.2f * x;
-            if (e.scale2) x = fmaf(x, s_par[2 * C + cb + c], s_par[3 * C + cb + c]);
-            f[c] = x;
+        // variants the planner emits (engine.cu build_plan): act 0/1/2, second affine only with ReLU (conv_11_a.2), +8 = lo plane;
+        // kMask limits what a kernel instantiates (code size), anything else runs the cold run-time variant
+#define DSU_EPI_CASE(N, A, S2, LO)                                                                          \
+    case N:                                                                                                 \
+        if constexpr ((kMask >> N) & 1u) { epilogue_batch<A, S2, LO>(p, s_par, v, opix, cb, tail, y3); break; } \
+        [[fallthrough]];
+        switch (variant) {
+            DSU_EPI_CASE(0, 0, 0, false)
+            DSU_EPI_CASE(1, 1, 0, false)
+            DSU_EPI_CASE(2, 2, 0, false)
+            DSU_EPI_CASE(5, 1, 1, false)
+            DSU_EPI_CASE(8, 0, 0, true)
+            DSU_EPI_CASE(9, 1, 0, true)
+            DSU_EPI_CASE(10, 2, 0, true)
+            DSU_EPI_CASE(13, 1, 1, true)
+            default: epilogue_batch<-1, -1, true>(p, s_par, v, opix, cb, tail, y3); break;
         }
-        if (e.resid_in) {
-            const float4* rp = reinterpret_cast<const float4*>(e.resid + opix * C + cb);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float4 rv = rp[c];
-                f[4 * c] += rv.x; f[4 * c + 1] += rv.y; f[4 * c + 2] += rv.z; f[4 * c + 3] += rv.w;
-            }
-        }
-        if (e.resid_out) {
-            float4* rp = reinterpret_cast<float4*>(e.resid + opix * C + cb);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) rp[c] = make_float4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]);
-        }
-        if (e.out2_hi) {
-            uint4* o = reinterpret_cast<uint4*>(e.out2_hi + opix * e.out2_pitch + e.out2_choff + cb);
-            uint4* ol = e.out2_lo ? reinterpret_cast<uint4*>(e.out2_lo + opix * e.out2_pitch + e.out2_choff + cb) : nullptr;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint4 hi, lo;
-                split8(f + 8 * c, hi, lo);
-                o[c] = hi;
-                if (ol) ol[c] = lo;
-            }
-        }
-        if (e.out_relu) {
-#pragma unroll
-            for (int c = 0; c < 32; ++c) f[c] = fmaxf(f[c], 0.0f);
-        }
-        if (e.out_hi) {
-            uint4* o = reinterpret_cast<uint4*>(e.out_hi + opix * e.out_pitch + e.out_choff + cb);
-            uint4* ol = e.out_lo ? reinterpret_cast<uint4*>(e.out_lo + opix * e.out_pitch + e.out_choff + cb) : nullptr;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint4 hi, lo;
-                split8(f + 8 * c, hi, lo);
-                o[c] = hi;
-                if (ol) ol[c] = lo;
-            }
-        }
-        if (tail) {
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                y3[0] = fmaf(f[c], s_par[4 * C + cb + c], y3[0]);
-                y3[1] = fmaf(f[c], s_par[5 * C + cb + c], y3[1]);
-                y3[2] = fmaf(f[c], s_par[6 * C + cb + c], y3[2]);
-            }
-        }
+#undef DSU_EPI_CASE
     }
     if (tail && pix_ok) {
         const size_t plane = static_cast<size_t>(p.Hout) * p.Wout;

@@ -56,6 +56,7 @@ struct LayerDef {
     int resid_in = 0, resid_out = 0, final = 0;
     int halo = 0;          // plain stride-1 conv run by the halo-reuse kernel (conv_halo.cu)
     int expanded = 0;      // stage-1 conv0: the 9 RIC taps were materialised by ric_expand -> 1x1 contraction
+    int first = 0;         // one 8-channel group per tap, stride 1: im2col from a shared-memory halo (conv_first.cu)
     // compiled at finalize
     int nchunks = 0, nblocks = 0;
     uint32_t kmask_full = 0xF, kmask_last = 0xF, kmask2_full = 0, kmask2_last = 0;
@@ -315,14 +316,24 @@ int compile_layer(dsu_engine* E, LayerDef& L) {
         }
         L.nblocks = static_cast<int>(chunks.size());
     } else if (!L.ric && !L.halo) {
+        // single 8-channel group per tap (conv0 of GeneratorJ), fp16 mode: one chunk per KERNEL ROW (slot j = tap (kh, j)),
+        // the layout the im2col-free kernel (conv_first.cu) needs; the tap-mode kernel runs the same table
+        L.first = (!exact && L.stride == 1 && L.up == 0 && L.segs.size() == 1 && L.segs[0].nch <= 8 && k > 3 && k <= 8 &&
+                   L.pad == (k - 1) / 2) ? 1 : 0;
         std::vector<HSlot> all;
-        for (int kh = 0; kh < k; ++kh)
+        for (int kh = 0; kh < k; ++kh) {
             for (int kw = 0; kw < k; ++kw)
                 for (size_t si = 0; si < L.segs.size(); ++si) {
                     const SegDef& s = L.segs[si];
                     for (int c8 = 0; c8 < s.nch; c8 += 8)
                         all.push_back(HSlot{kh, kw, (int)si, s.choff + c8, s.wch0 + c8, std::max(0, std::min(8, s.wn - c8))});
                 }
+            if (L.first) {
+                push_dev_slots(all);
+                chunks.push_back(all);
+                all.clear();
+            }
+        }
         for (size_t i = 0; i < all.size(); i += dpc) {
             std::vector<HSlot> ds(all.begin() + i, all.begin() + std::min(all.size(), i + dpc));
             push_dev_slots(ds);
@@ -557,6 +568,8 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
     size_t step_idx = 0;
     int ric_persist_mode = 2;     // 0 never, 1 Cout <= 64, 2 all RIC layers (measured best: profiles/r01j)
     if (const char* ev = std::getenv("DSU_RIC_PERSIST")) ric_persist_mode = std::atoi(ev);
+    int first_mode = 1;           // 0: conv0 of GeneratorJ stays in tap mode (conv_umma.cu), 1: conv_first.cu
+    if (const char* ev = std::getenv("DSU_FIRST")) first_mode = std::atoi(ev);
     for (const Step& sp : E->steps) {
         if (evs) CUDA_TRY(cudaEventRecord((*evs)[step_idx], st));
         ++step_idx;
@@ -675,7 +688,34 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
             p.tmem_cols = cols;
             CUDA_TRY(launch_conv_ric_persist(p, st));
         } else {
-            CUDA_TRY(launch_conv(p, st));
+            bool first = false;
+            if (L.first && first_mode != 0) {
+                // im2col-free persistent kernel: ring of pixel-linear halo tiles + the whole weight matrix in shared memory
+                p.ksize = L.k; p.pad = L.pad;
+                p.halo_w = 16;
+                p.halo_rows = 16 + L.k - 1;
+                p.halo_bytes = p.halo_rows * 16 * 16;
+                const int ks_max = std::min(4, std::min(L.k, 256 / L.cout));
+                p.ks = std::min(2, ks_max);
+                if (const char* ev = std::getenv("DSU_FIRST_KS")) p.ks = std::max(1, std::min(ks_max, std::atoi(ev)));
+                const int left = 227 * 1024 - L.nchunks * p.b_bytes - 8 * 1024;
+                p.sa = std::min(4, left / p.halo_bytes);
+                if (const char* ev = std::getenv("DSU_FIRST_NA")) p.sa = std::max(2, std::min(6, std::min(left / p.halo_bytes, std::atoi(ev))));
+                if (p.ks >= 1 && p.sa >= 2) {
+                    p.ns = 4 * p.ks * L.cout <= 512 ? 4 : 2;          // accumulator sets in TMEM
+                    if (const char* ev = std::getenv("DSU_FIRST_SETS")) p.ns = (std::atoi(ev) >= 4 && p.ns == 4) ? 4 : 2;
+                    cols = 32;
+                    while (cols < p.ns * p.ks * L.cout) cols *= 2;
+                    p.tmem_cols = cols;
+                    first = true;
+                }
+            }
+            if (first) CUDA_TRY(launch_conv_first(p, st));
+            else {
+                pick_stages(false, p.b_bytes, &p.sa, &p.sb);
+                p.ks = 1;
+                CUDA_TRY(launch_conv(p, st));
+            }
         }
     }
     if (evs) CUDA_TRY(cudaEventRecord((*evs)[step_idx], st));

@@ -127,6 +127,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr, uint32_t 
     d |= static_cast<uint64_t>(4) << 61;                 // SWIZZLE_64B
     return d;
 }
+// K-major operand WITHOUT swizzle: 8-row x 16-byte core matrices.  Measured (tools/umma_probe_ns.cu): the MMA reads
+//     addr(row, k) = start + (row / 8) * sbo + (k / 8) * lbo + (row % 8) * 16 + (k % 8) * 2
+// for any 16-byte-aligned start and any 16-byte-multiple lbo / sbo, overlapping core matrices included - so
+// lbo = 16 over a pixel-linear buffer (16 B per pixel) makes "the next 8 K elements" simply "the next pixel".
+__device__ __forceinline__ uint64_t umma_desc_noswizzle(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    return d;
+}
 // Instruction descriptor: fp16 A/B (K-major), fp32 D, M x N tile.
 __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t m, uint32_t n) {
     return (1u << 4) | ((n >> 3) << 17) | ((m >> 4) << 24);

@@ -89,12 +89,11 @@ __device__ __forceinline__ void ric_produce(const ConvParams& p, uint8_t* a_smem
         auto blend_item = [&](int i, const uint4 (&nb)[9], const uint4 (&nbl)[9], const float2 (&lyx)[8], int oct) {
             const int r = prow + 32 * i;
             // first item of a block: the previous block's MMAs must have drained the tap buffers
-            if (g0 + b > 0 && i == i_lo) {      // one lane polls the 9 barriers, __syncwarp publishes the acquire to the warp
-                if ((tid & 31) == 0) {
+            if (g0 + b > 0 && i == i_lo) {
+                // every lane polls (warp-uniform): a single polling lane followed by __syncwarp parks the other 31 lanes on a
+                // WARPSYNC while lane 0 sleeps in NANOSLEEP.SYNCS - measured 5 % slower on upconv1 (profiles/r01m_ric_upconv1.ncu-rep)
 #pragma unroll 1
-                    for (int t = 0; t < 9; ++t) mbar_wait(bar_empty_a + 8 * t, (g0 + b - 1) & 1);
-                }
-                __syncwarp();
+                for (int t = 0; t < 9; ++t) mbar_wait(bar_empty_a + 8 * t, (g0 + b - 1) & 1);
             }
             uint8_t* rowp = a_smem + r * 128;
             // ---- centre tap (raster tap 4): the pixel itself
