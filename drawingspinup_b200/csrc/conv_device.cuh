@@ -58,19 +58,30 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 // 32 channels of one pixel -> fp16 NHWC (hi plane, plus the split-fp16 lo plane when kLo and `lo` is non-null)
 template <bool kLo>
 __device__ __forceinline__ void store32(__half* hi, __half* lo, const float* f) {
-    uint4* o = reinterpret_cast<uint4*>(hi);
+    // 32-byte aligned destinations (every buffer whose pixel pitch and channel offset are multiples of 16 channels) take
+    // two 256-bit stores; the address test is warp-uniform for such buffers
+    const bool wide = (reinterpret_cast<uintptr_t>(hi) & 31u) == 0;
     if (kLo && lo) {
-        uint4* ol = reinterpret_cast<uint4*>(lo);
+        uint4 h[4], l[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            uint4 h, l;
-            split8(f + 8 * c, h, l);
-            o[c] = h;
-            ol[c] = l;
+        for (int c = 0; c < 4; ++c) split8(f + 8 * c, h[c], l[c]);
+        if (wide) {
+            st_global_256(hi, h[0], h[1]); st_global_256(hi + 16, h[2], h[3]);
+            st_global_256(lo, l[0], l[1]); st_global_256(lo + 16, l[2], l[3]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { reinterpret_cast<uint4*>(hi)[c] = h[c]; reinterpret_cast<uint4*>(lo)[c] = l[c]; }
         }
     } else {
+        uint4 h[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) o[c] = pack8(f + 8 * c);
+        for (int c = 0; c < 4; ++c) h[c] = pack8(f + 8 * c);
+        if (wide) {
+            st_global_256(hi, h[0], h[1]); st_global_256(hi + 16, h[2], h[3]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) reinterpret_cast<uint4*>(hi)[c] = h[c];
+        }
     }
 }
 
@@ -187,10 +198,11 @@ __device__ __forceinline__ void epilogue_row(const ConvParams& p, const float* s
         if (!pix_ok) continue;
         // variants the planner emits (engine.cu build_plan): act 0/1/2, second affine only with ReLU (conv_11_a.2), +8 = lo plane;
         // kMask limits what a kernel instantiates (code size), anything else runs the cold run-time variant
-#define DSU_EPI_CASE(N, A, S2, LO)                                                                          \
-    case N:                                                                                                 \
-        if constexpr ((kMask >> N) & 1u) { epilogue_batch<A, S2, LO>(p, s_par, v, opix, cb, tail, y3); break; } \
-        [[fallthrough]];
+#define DSU_EPI_CASE(N, A, S2, LO)                                                                                        \
+    case N:                                                                                                               \
+        if constexpr ((kMask >> N) & 1u) { epilogue_batch<A, S2, LO>(p, s_par, v, opix, cb, tail, y3); handled = true; } \
+        break;
+        bool handled = false;
         switch (variant) {
             DSU_EPI_CASE(0, 0, 0, false)
             DSU_EPI_CASE(1, 1, 0, false)
@@ -200,8 +212,9 @@ __device__ __forceinline__ void epilogue_row(const ConvParams& p, const float* s
             DSU_EPI_CASE(9, 1, 0, true)
             DSU_EPI_CASE(10, 2, 0, true)
             DSU_EPI_CASE(13, 1, 1, true)
-            default: epilogue_batch<-1, -1, true>(p, s_par, v, opix, cb, tail, y3); break;
+            default: break;
         }
+        if (!handled) epilogue_batch<-1, -1, true>(p, s_par, v, opix, cb, tail, y3);
 #undef DSU_EPI_CASE
     }
     if (tail && pix_ok) {

@@ -119,7 +119,7 @@ conv_ric_persist_kernel(const __grid_constant__ ConvParams p) {
             const int set = it & 1;
             mbar_wait(bar_acc_full + 8 * set, (it >> 1) & 1);
             tc_fence_after();
-            epilogue_row<(kMode == 2 ? kEpiSplit : kEpiFp16) & 0x0707u>(p, s_par, tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(set * NI * C), n,
+            epilogue_row<(kMode == 2 ? 0x0702u : 0x0007u)>(p, s_par, tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(set * NI * C), n,
                          ty0 + (r >> 4), tx0 + (r & 15), 0, NI, C, 1);
             tc_fence_before();
             mbar_arrive(bar_acc_empty + 8 * set);

@@ -153,7 +153,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         {
             const int quad = warp & 3;
             const int r = quad * 32 + lane;      // accumulator row = TMEM lane = patch pixel
-            epilogue_row<kMode == 0 ? kEpiAll : ((kMode == 2 ? kEpiSplit : kEpiFp16) & 0x0707u)>(p, s_par, tmem_base + (static_cast<uint32_t>(quad * 32) << 16), n, ty0 + (r >> 4), tx0 + (r & 15), warp >> 2,
+            epilogue_row<kMode == 0 ? kEpiAll : ((kMode == 2 ? 0x0702u : 0x0007u))>(p, s_par, tmem_base + (static_cast<uint32_t>(quad * 32) << 16), n, ty0 + (r >> 4), tx0 + (r & 15), warp >> 2,
                          kRic ? p.ks : 1, C);
         }
         tc_fence_before();

@@ -665,8 +665,8 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
             // persistent CTAs with double-buffered accumulators when two accumulator sets fit in TMEM
             const bool persist = persist_mode != 0 && 2 * p.ns * p.ks * L.cout <= 512;
             p.tps = 1;
-            if (persist) {   // taps per weight stage: 2 when the ring stays >= 3 stages deep (per K-split group)
-                int tps = 2;
+            if (persist) {   // taps per weight stage: up to 3 while the ring stays >= 3 stages deep (per K-split group)
+                int tps = 3;
                 if (const char* ev = std::getenv("DSU_HALO_TPS")) tps = std::max(1, std::min(4, std::atoi(ev)));
                 const int left = 227 * 1024 - p.sa * p.halo_bytes - 8 * 1024;
                 while (tps > 1 && (left / (tps * p.b_bytes)) / p.ks < 3) --tps;

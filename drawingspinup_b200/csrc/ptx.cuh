@@ -104,6 +104,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// 256-bit global store (STG.E.ENL2.256, sm_100+): one full 32-byte sector per thread, so a strided NHWC epilogue does not
+// leave half-written sectors for L2 to complete with a DRAM read (profiles/r01m_conv_first*.ncu-rep: dram read = input + output)
+__device__ __forceinline__ void st_global_256(void* ptr, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
+                 "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+}
+
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle:
 // rows of 128 B (64 fp16), 8-row groups `sbo_bytes` apart.

@@ -32,9 +32,11 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     tot = sum(v[0] for v in agg.values())
     print(json.dumps({"total_ms": round(tot, 2), **{k: (round(v[0], 3), round(v[1] / max(v[0], 1e-9) / 1e9, 1)) for k, v in agg.items()}}))
 else:
-    combos = [(2, "fp16", "", ""), (1, "fp16", "", ""), (2, "fp16x3", "", ""), (1, "fp16x3", "", "")]
-    for stage, prec, ns, ks in combos:
-        env = dict(os.environ, **({'DSU_HALO_NS': ns, 'DSU_HALO_KS': ks} if ns else {}), SWEEP_STAGE=str(stage), SWEEP_PREC=prec)
+    combos = [(2, "fp16", "", "", ""), (2, "fp16", "2", "2", ""), (2, "fp16", "2", "1", ""), (2, "fp16", "1", "2", ""), (2, "fp16", "1", "4", ""),
+              (2, "fp16", "", "", "1"), (2, "fp16", "", "", "3"), (1, "fp16", "", "", ""), (2, "fp16x3", "", "", ""), (1, "fp16x3", "", "", "")]
+    for stage, prec, ns, ks, tps in combos:
+        env = dict(os.environ, **({'DSU_HALO_NS': ns, 'DSU_HALO_KS': ks} if ns else {}), **({'DSU_HALO_TPS': tps} if tps else {}),
+                   SWEEP_STAGE=str(stage), SWEEP_PREC=prec)
         out = subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=env, capture_output=True, text=True)
         line = out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-300:]
-        print("stage%d %-6s NS=%s KS=%s %s" % (stage, prec, ns, ks, line), flush=True)
+        print("stage%d %-6s NS=%s KS=%s TPS=%s %s" % (stage, prec, ns, ks, tps, line), flush=True)
