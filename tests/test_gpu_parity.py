@@ -97,6 +97,38 @@ def test_single_pass_fp16_error_bound(dev, stage):
     assert err.max().item() < TOL_FP16 and err.mean().item() < 2e-3
 
 
+@pytest.mark.parametrize("shape", [(1, 4, 4), (2, 20, 36), (3, 72, 100), (1, 132, 68)])
+def test_first_layer_kernel_matches_tap_mode_and_oracle(dev, shape, monkeypatch):
+    """GeneratorJ.conv0 (models.py:44-46) in fp16 mode runs the im2col-free kernel (conv_first.cu: no-swizzle UMMA
+    operand read from the halo tile); DSU_FIRST=0 sends it through the tap-mode kernel.  Both compute the same fp16
+    products with fp32 accumulation, so conv0 may differ by accumulation order only (<= 1 fp16 ulp of its range)."""
+    b, h, w = shape
+    m, sd = _model(2, dev, precision="fp16")
+    x = _frames_tensor(b, h, w, seed=11, stage=2)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("DSU_FIRST", mode)
+        with torch.no_grad():
+            y = m(x.to(dev)).cpu()
+        out[mode] = (y, m.debug_buffer(0, 0, (b, h, w, 40)).float()[..., :32])
+    assert (out["0"][1] - out["1"][1]).abs().max().item() <= 2 ** -7       # conv0 activations (|v| < 8): one fp16 ulp
+    ref = _oracle(2, sd, x)
+    for mode in ("0", "1"):
+        assert (out[mode][0] - ref).abs().max().item() < TOL_FP16
+
+
+@pytest.mark.parametrize("width", [64, 128])
+def test_first_layer_kernel_wider_outputs(dev, width):
+    """filters[0] = 64 / 128: the first-layer kernel with 2 (resp. 1) K-split issuers and 4 (resp. 2) accumulator sets."""
+    args = dict(DEFAULT_ARGS, filters=[width, 64, 128, 128, 128, 64], resnet_blocks=1)
+    m, sd = _model(2, dev, precision="fp16", args=args)
+    x = _frames_tensor(2, 40, 24, seed=5, stage=2)
+    with torch.no_grad():
+        y = m(x.to(dev)).cpu()
+    err = (y - _oracle(2, sd, x, args)).abs()
+    assert err.max().item() < TOL_FP16
+
+
 @pytest.mark.parametrize("stage", [1, 2])
 def test_nondefault_offsets_builtin_table(dev, stage):
     """The engine's own generate_coordinates restatement (no torch offsets supplied) also meets parity."""
