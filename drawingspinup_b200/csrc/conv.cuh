@@ -107,6 +107,7 @@ cudaError_t launch_conv(const ConvParams& p, cudaStream_t stream);
 cudaError_t launch_conv_halo(const ConvParams& p, cudaStream_t stream);
 cudaError_t launch_conv_halo_persist(const ConvParams& p, cudaStream_t stream);
 cudaError_t launch_conv_ric_persist(const ConvParams& p, cudaStream_t stream);
+// first-layer kernel (conv_first.cu): reuses sa = halo buffers, ks = issuers, ns = accumulator sets, ksize / pad / halo_rows / halo_bytes
 cudaError_t launch_conv_first(const ConvParams& p, cudaStream_t stream);
 size_t conv_halo_smem_bytes(const ConvParams& p);
 size_t conv_smem_bytes(const ConvParams& p);

@@ -17,9 +17,9 @@
 //   * the producer warps then become the epilogue: tcgen05.ld the accumulator row of their pixel,
 //     apply folded BN / activation / residual, write fp16 NHWC (hi [+lo] planes), the fp32 residual
 //     stream, or the fused conv_12 1x1 + tanh + uint8 composite tail.
-// "Exact" mode (split fp16): a K chunk holds 32 channels as [a_hi | a_lo]; it is multiplied by
-// [W_hi | W_hi] (4 K-steps) and its hi half again by W_lo (2 K-steps) into the same accumulator:
-// a_hi*W_hi + a_lo*W_hi + a_hi*W_lo, fp32-grade products at 3x the tensor work.
+// "Exact" mode (split fp16): a K chunk holds 32 channels as [a_hi | a_lo], its weight tile [W_hi | W_lo] in one
+// 128-byte row; A steps 0-3 are issued against B steps 0,1,0,1 and A steps 0,1 again against B steps 2,3 into the
+// same accumulator: a_hi*W_hi + a_lo*W_hi + a_hi*W_lo, fp32-grade products at 3x the tensor work.
 #include "conv_device.cuh"
 #include "ric_producer.cuh"
 

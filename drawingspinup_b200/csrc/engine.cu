@@ -298,7 +298,7 @@ int compile_layer(dsu_engine* E, LayerDef& L) {
         }
     };
     // halo-reuse kernel: plain stride-1 convs with >= 32 channels per tap (the 8-channel 7x7 conv0 was measured slower
-    // there: 49 single-K-step MMAs per tile; it stays in tap mode where 8 taps share one 64-element chunk)
+    // there: 49 single-K-step MMAs per tile; it has its own kernel, conv_first.cu, and the tap-mode kernel as fallback)
     L.halo = (!L.ric && !L.expanded && L.stride == 1 && real_k / (k * k) >= 32) ? 1 : 0;
     if (L.expanded) {
         // data slot = (tap, 8-channel group) of the expanded buffer [pix][tap * nch + c]; weights keep their 3x3 index.
