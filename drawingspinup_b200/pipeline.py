@@ -99,12 +99,19 @@ class StylizationPipeline:
         return (out, mid) if keep_stage1 else out
 
     @torch.no_grad()
-    def run_host(self, color: torch.Tensor, pos: torch.Tensor, edge: torch.Tensor, out: torch.Tensor):
+    def run_host(self, color: torch.Tensor, pos: torch.Tensor, edge: torch.Tensor, out: torch.Tensor,
+                 keep_stage1: bool = False):
         """Same from / to HOST (pinned) uint8 stacks: per batch the inputs are copied to the device,
         both stages run, and the stage-2 RGBA result is copied back (``out`` is filled in place).
         Copies run on a second stream so that the upload of batch i+1 and the download of batch i-1
-        overlap the kernels of batch i (frames are independent, so this is plain double buffering)."""
+        overlap the kernels of batch i (frames are independent, so this is plain double buffering).
+        Returns ``out``; with ``keep_stage1`` the stage-1 RGBA frames (what test_stage1.py writes to
+        ``res_stage1_mask_pos``) are downloaded as well and returned instead."""
         n = color.shape[0]
+        mid = None
+        if keep_stage1:
+            mid = torch.empty_like(out)
+            mid = mid.pin_memory() if out.is_pinned() else mid
         main = torch.cuda.current_stream(self.device)
         if not hasattr(self, "_copy_stream"):
             self._copy_stream = torch.cuda.Stream(self.device)
@@ -133,13 +140,17 @@ class StylizationPipeline:
             with torch.cuda.stream(cs):
                 cs.wait_event(done)
                 out[lo:hi].copy_(r2, non_blocking=True)
+                if mid is not None:
+                    mid[lo:hi].copy_(r1, non_blocking=True)
             for t in (c, p, e):
                 t.record_stream(main)          # allocated on the copy stream, consumed by the kernels
             r2.record_stream(cs)               # produced on the main stream, downloaded on the copy stream
+            if mid is not None:
+                r1.record_stream(cs)
             pending.append((c, p, e, r1, r2))
         cs.synchronize()
         main.synchronize()
-        return out
+        return mid if keep_stage1 else out
 
     def flops_per_frame(self, h: int, w: int) -> float:
         return self.g1.algorithmic_flops(1, h, w) + self.g2.algorithmic_flops(1, h, w)

@@ -135,3 +135,31 @@ def make_state_dict(stage: int, seed: int = 1234, filters: Sequence[int] = DEFAU
 def to_torch_state_dict(sd_np: Dict[str, np.ndarray]):
     import torch
     return OrderedDict((k, torch.from_numpy(np.array(v, copy=True, order='C'))) for k, v in sd_np.items())
+
+
+def write_character_tree(root_dir: str, uid: str, actions: Dict[str, int], height: int, width: int, seed: int = 1234,
+                         state_dicts=None, frames=None) -> Dict[str, Tuple[np.ndarray, np.ndarray, np.ndarray]]:
+    """Materialise a synthetic character in the reference's on-disk layout (README.md "dataset" tree):
+    ``<root>/<uid>/mesh/blender_render/<action>/{color,pos,edge}/NNNN.png`` for ``actions = {name: n_frames}`` and,
+    when ``state_dicts = (sd_stage1, sd_stage2)`` (torch tensors) is given, the two ``model_99999.pth`` checkpoints.
+    ``frames[action] = (color, pos, edge)`` overrides the generated stacks.  Returns the stacks per action."""
+    import os
+    from PIL import Image
+    out = {}
+    base = os.path.join(root_dir, uid, "mesh")
+    for ai, (action, n) in enumerate(sorted(actions.items())):
+        color, pos, edge = frames[action] if frames and action in frames else make_frames(n, height, width, seed=seed + ai)
+        for sub in ("color", "pos", "edge"):
+            os.makedirs(os.path.join(base, "blender_render", action, sub), exist_ok=True)
+        for i in range(color.shape[0]):
+            name = "%04d.png" % i
+            Image.fromarray(color[i]).save(os.path.join(base, "blender_render", action, "color", name))
+            Image.fromarray(pos[i]).save(os.path.join(base, "blender_render", action, "pos", name))
+            Image.fromarray(edge[i]).save(os.path.join(base, "blender_render", action, "edge", name))
+        out[action] = (color, pos, edge)
+    if state_dicts is not None:
+        import torch
+        for log, sd in zip(("logs_stage1_mask_pos", "logs_stage2_mask_pos_edge"), state_dicts):
+            os.makedirs(os.path.join(base, log), exist_ok=True)
+            torch.save(sd, os.path.join(base, log, "model_99999.pth"))
+    return out
