@@ -101,6 +101,10 @@ struct ConvParams {
     const uint8_t* ric_oct; // [Hout*Wout]
     const uint2* ric_wh;    // [Hout*Wout][8] the 4 bilinear weights of each rotated tap as fp16 {w00,w01 | w10,w11} (packed-half2 blend)
     EpiParams epi;
+    // sub-pixel class of a fused nearest-x2 + 3x3 convolution (experimental, DSU_SUBPIXEL=1; conv_halo_persist_kernel<true>):
+    // the launch is a 2x2 convolution over the LOW-resolution source with asymmetric padding (pad_y, pad_x) whose output
+    // pixel (oy, ox) of the Hout x Wout grid lands at (2*oy + sub_py, 2*ox + sub_px) of the (2*Hout) x (2*Wout) output buffer
+    int sub, sub_py, sub_px, pad_y, pad_x;
 };
 
 cudaError_t launch_conv(const ConvParams& p, cudaStream_t stream);

@@ -168,13 +168,15 @@ __device__ __forceinline__ void epilogue_batch(const ConvParams& p, const float*
 // warp-collective); chalf is warp-uniform.
 // `nsplit` partial accumulators `split_stride` columns apart (K-split issuers) are summed first.
 constexpr uint32_t kEpiAll = 0xFFFFu, kEpiFp16 = 0x0027u, kEpiSplit = 0x2700u;   // variant masks (bit = variant index)
-template <uint32_t kMask = kEpiAll>
+template <uint32_t kMask = kEpiAll, bool kSub = false>
 __device__ __forceinline__ void epilogue_row(const ConvParams& p, const float* s_par, uint32_t t_addr,
                                              int n, int oy, int ox, int chalf, int nsplit = 1, int split_stride = 0, int csplit = 2) {
     const EpiParams& e = p.epi;
     const int C = p.Cout;
     const bool pix_ok = oy < p.Hout && ox < p.Wout;
-    const size_t opix = (static_cast<size_t>(n) * p.Hout + oy) * p.Wout + ox;
+    // kSub: (oy, ox) index the low-resolution grid of one sub-pixel class; the output buffer is twice as large in y and x
+    const size_t opix = kSub ? (static_cast<size_t>(n) * (2 * p.Hout) + (2 * oy + p.sub_py)) * (2 * p.Wout) + (2 * ox + p.sub_px)
+                             : (static_cast<size_t>(n) * p.Hout + oy) * p.Wout + ox;
     const int ncb = C / 32;
     const bool tail = e.w12 != nullptr;
     const int cb_first = tail ? 0 : chalf, cb_step = tail ? 1 : csplit;   // csplit warps share a lane quadrant

@@ -32,6 +32,9 @@ __host__ __device__ inline PersistSmem persist_smem(int na, int halo_bytes, int 
 
 }  // namespace
 
+// kSub = true: one sub-pixel class of a fused nearest-x2 + 3x3 convolution (see ConvParams::sub) - the halo origin uses the
+// asymmetric (pad_y, pad_x) and the epilogue scatters to every second output pixel; everything else is the same kernel.
+template <bool kSub>
 __global__ void __launch_bounds__(kThreadsHalo, 1)
 conv_halo_persist_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -115,7 +118,7 @@ conv_halo_persist_kernel(const __grid_constant__ ConvParams p) {
                 const uint32_t dst0 = base + L.a0 + s * p.halo_bytes;
                 for (int row = tid >> 3; row < HR; row += kProd / 8) {
                     const int hy = row / HW, hx = row - hy * HW;
-                    const int vy = ty0 - p.pad + hy, vx = tx0 - p.pad + hx;
+                    const int vy = ty0 - (kSub ? p.pad_y : p.pad) + hy, vx = tx0 - (kSub ? p.pad_x : p.pad) + hx;
                     const bool ok = sl.valid && static_cast<unsigned>(vy) < static_cast<unsigned>(p.Hv) &&
                                     static_cast<unsigned>(vx) < static_cast<unsigned>(p.Wv);
                     const size_t pix = frame_in + static_cast<size_t>(vy >> p.up) * p.Win + (vx >> p.up);
@@ -140,7 +143,7 @@ conv_halo_persist_kernel(const __grid_constant__ ConvParams p) {
             tc_fence_after();
             const uint32_t t_set = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(set * NI * C);
             for (int s = 0; s < NS; ++s)
-                epilogue_row(p, s_par, t_set + s * C, n, ty0 + (r >> 3), tx0 + 8 * s + (r & 7), 0, KS, NS * C, 1);
+                epilogue_row<kEpiAll, kSub>(p, s_par, t_set + s * C, n, ty0 + (r >> 3), tx0 + 8 * s + (r & 7), 0, KS, NS * C, 1);
             tc_fence_before();
             mbar_arrive(bar_acc_empty + 8 * set);        // this accumulator set may be overwritten
         }
@@ -257,7 +260,9 @@ cudaError_t launch_conv_halo_persist(const ConvParams& p, cudaStream_t stream) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 64 && !attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(conv_halo_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(conv_halo_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(conv_halo_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         e = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
@@ -270,7 +275,13 @@ cudaError_t launch_conv_halo_persist(const ConvParams& p, cudaStream_t stream) {
         return cudaErrorInvalidConfiguration;
     const int tiles = ((p.Wout + 8 * p.ns - 1) / (8 * p.ns)) * ((p.Hout + 15) / 16) * p.B;
     const int ctas = tiles < sm_count[dev < 64 ? dev : 0] ? tiles : sm_count[dev < 64 ? dev : 0];
-    conv_halo_persist_kernel<<<ctas, kThreadsHalo, conv_halo_persist_smem_bytes(p), stream>>>(p);
+    if (p.sub) {
+        if (p.up != 0 || p.ksize != 2 || p.pad_y < 0 || p.pad_y > 1 || p.pad_x < 0 || p.pad_x > 1 || (p.sub_py | p.sub_px) & ~1)
+            return cudaErrorInvalidConfiguration;
+        conv_halo_persist_kernel<true><<<ctas, kThreadsHalo, conv_halo_persist_smem_bytes(p), stream>>>(p);
+    } else {
+        conv_halo_persist_kernel<false><<<ctas, kThreadsHalo, conv_halo_persist_smem_bytes(p), stream>>>(p);
+    }
     return cudaGetLastError();
 }
 

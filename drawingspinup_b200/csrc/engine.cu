@@ -57,6 +57,11 @@ struct LayerDef {
     int halo = 0;          // plain stride-1 conv run by the halo-reuse kernel (conv_halo.cu)
     int expanded = 0;      // stage-1 conv0: the 9 RIC taps were materialised by ric_expand -> 1x1 contraction
     int first = 0;         // one 8-channel group per tap, stride 1: im2col from a shared-memory halo (conv_first.cu)
+    // experimental (DSU_SUBPIXEL=1): sub-pixel class py*2+px of a nearest-x2 + 3x3 convolution (models.py:180-192):
+    // out(2y+py, 2x+px) = sum over a,b in {0,1} of Wc[a][b] * in(y+a-1+py, x+b-1+px), Wc = sums of the 3x3 taps that hit the
+    // same source pixel - exact including the zero border, 4 taps instead of 9 per output pixel.  k = 2 for such a layer and
+    // wk = 3 is the kernel size of the stored weights; -1 = ordinary layer
+    int sub = -1, wk = 0;
     // compiled at finalize
     int nchunks = 0, nblocks = 0;
     uint32_t kmask_full = 0xF, kmask_last = 0xF, kmask2_full = 0, kmask2_last = 0;
@@ -217,17 +222,31 @@ int build_plan(dsu_engine* E) {
         Bl.out_buf = TT; Bl.out_relu = (i + 1 < c.resnet_blocks) ? 1 : 0;
         add(Bl);
     }
+    // plain (stage-2) up-convolutions can run as four sub-pixel 2x2 convolutions on the low-resolution source (2.25x fewer
+    // MACs); experimental until validated on hardware, so only with DSU_SUBPIXEL=1 in the environment of dsu_create
+    const char* sub_env = std::getenv("DSU_SUBPIXEL");
+    const bool subpixel = !ric && sub_env && std::atoi(sub_env) != 0;
+    auto add_up = [&](LayerDef L) {
+        if (!subpixel) { L.up = 1; add(L); return; }
+        const std::string base = L.name;
+        for (int cls = 0; cls < 4; ++cls) {
+            LayerDef S = L;
+            S.name = base + ".s" + std::to_string(cls);
+            S.up = 0; S.sub = cls; S.wk = 3; S.k = 2; S.pad = 0;
+            add(S);
+        }
+    };
     {
         LayerDef L; L.name = "upconv2"; L.wkey = "upconv2.1.weight"; L.bn = bn ? "upconv2.2" : "";
-        L.up = 1; L.ric = ric; L.cout = f[4]; L.level_out = 1;
+        L.ric = ric; L.cout = f[4]; L.level_out = 1;
         L.segs = {{has_res ? TT : O2, 0, f[2], 0, f[2]}, {O2, 0, f[2], f[3], f[2]}}; L.act = 1; L.out_buf = V2;
-        add(L);
+        add_up(L);
     }
     {
         LayerDef L; L.name = "upconv1"; L.wkey = "upconv1.1.weight"; L.bn = bn ? "upconv1.2" : "";
-        L.up = 1; L.ric = ric; L.cout = f[4]; L.level_out = 0;
+        L.ric = ric; L.cout = f[4]; L.level_out = 0;
         L.segs = {{V2, 0, f[4], 0, f[4]}, {O1, 0, f[1], f[4], f[1]}}; L.act = 1; L.out_buf = V1;
-        add(L);
+        add_up(L);
     }
     {
         LayerDef L; L.name = "conv_11"; L.wkey = "conv_11.0.weight"; L.bkey = bias_of("conv_11.0");
@@ -265,9 +284,35 @@ int upload(T** dst, const std::vector<T>& src) {
 int compile_layer(dsu_engine* E, LayerDef& L) {
     const bool exact = E->exact;
     const int C = L.cout, k = L.k;
-    const std::vector<float>& Wt = E->w.at(L.wkey);
     int cin_total = 0;
     for (const SegDef& s : L.segs) cin_total = std::max(cin_total, s.wch0 + s.wn);
+    std::vector<float> Wsub;
+    if (L.sub >= 0) {
+        // 2x2 weights of sub-pixel class (py, px): tap a of an even output row (py = 0) collects kernel rows {0} / {1,2}, of an
+        // odd row {0,1} / {2} (the rows of the nearest-x2 image that map to source row y+a-1+py); same for columns
+        const std::vector<float>& W3 = E->w.at(L.wkey);
+        if (L.wk != 3 || k != 2 || W3.size() != static_cast<size_t>(C) * cin_total * 9)
+            return fail(DSU_E_INVALID, "weight size mismatch for " + L.wkey);
+        const int py = L.sub >> 1, px = L.sub & 1;
+        auto members = [](int parity, int tap, int* lo, int* hi) {
+            if (parity == 0) { *lo = tap == 0 ? 0 : 1; *hi = tap == 0 ? 0 : 2; }
+            else { *lo = tap == 0 ? 0 : 2; *hi = tap == 0 ? 1 : 2; }
+        };
+        Wsub.assign(static_cast<size_t>(C) * cin_total * 4, 0.0f);
+        for (int o = 0; o < C; ++o)
+            for (int c = 0; c < cin_total; ++c)
+                for (int a = 0; a < 2; ++a)
+                    for (int b = 0; b < 2; ++b) {
+                        int r0, r1, c0, c1;
+                        members(py, a, &r0, &r1);
+                        members(px, b, &c0, &c1);
+                        double acc = 0;
+                        for (int kh = r0; kh <= r1; ++kh)
+                            for (int kw = c0; kw <= c1; ++kw) acc += W3[((static_cast<size_t>(o) * cin_total + c) * 3 + kh) * 3 + kw];
+                        Wsub[((static_cast<size_t>(o) * cin_total + c) * 2 + a) * 2 + b] = static_cast<float>(acc);
+                    }
+    }
+    const std::vector<float>& Wt = L.sub >= 0 ? Wsub : E->w.at(L.wkey);
     if (Wt.size() != static_cast<size_t>(C) * cin_total * k * k) return fail(DSU_E_INVALID, "weight size mismatch for " + L.wkey);
 
     // A "data slot" is 8 input channels of one concat segment at one tap.  A chunk (8 smem slots =
@@ -281,6 +326,8 @@ int compile_layer(dsu_engine* E, LayerDef& L) {
     double real_k = 0;
     for (const SegDef& s : L.segs) real_k += static_cast<double>(s.wn) * k * k;
     L.macs_per_px = real_k * C;
+    // algorithmic work of a sub-pixel class = a quarter of the 3x3 layer's output pixels (flops are reported per output pixel of level_out)
+    if (L.sub >= 0) L.macs_per_px = real_k / 4.0 * 9.0 / 4.0 * C;
     auto dev_slot = [&](const HSlot& h, bool lo_plane) {
         Slot sl{};
         sl.dy = static_cast<int8_t>(L.expanded ? 0 : h.kh - L.pad);
@@ -586,7 +633,9 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
         }
         const LayerDef& L = E->layers[sp.layer];
         ConvParams p{};
-        p.B = B; p.Hout = H >> L.level_out; p.Wout = W >> L.level_out;
+        // a sub-pixel class iterates over the low-resolution grid (one level below its output buffer)
+        const int grid_level = L.level_out + (L.sub >= 0 ? 1 : 0);
+        p.B = B; p.Hout = H >> grid_level; p.Wout = W >> grid_level;
         const int src_level = E->buf_level[L.segs[0].buf];
         p.Hin = H >> src_level; p.Win = W >> src_level;
         p.up = L.up; p.Hv = p.Hin << L.up; p.Wv = p.Win << L.up;
@@ -634,6 +683,11 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
             // 2 halo buffers + as many weight stages as fit
             const int kk = L.expanded ? 1 : L.k, pp = L.expanded ? 0 : L.pad;     // expanded conv0 = 1x1 over the tap-expanded buffer
             p.halo = 1; p.ksize = kk; p.pad = pp;
+            if (L.sub >= 0) {
+                p.sub = 1; p.sub_py = L.sub >> 1; p.sub_px = L.sub & 1;
+                p.pad_y = 1 - p.sub_py; p.pad_x = 1 - p.sub_px;
+            }
+            const int halo_extra = L.sub >= 0 ? kk - 1 : 2 * pp;     // halo pixels beyond the output tile, per axis
             // candidates in order of measured preference (profiles/r01d sweep): wide CTAs for 3x3 (weight-tile reuse),
             // sub-tile x K-split for 7x7 (halo size); the first that fits TMEM and shared memory wins
             // {sub-tiles, K-split issuers, halo buffers}
@@ -651,8 +705,8 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
                 if (ns * ks > kIssuersHalo || ns * ks * L.cout > 512 || ks > kk * kk) continue;
                 if (persist_mode == 2 && 2 * ns * ks * L.cout > 512) continue;     // only configurations that can double-buffer TMEM
                 p.ns = ns; p.ks = ks;
-                p.halo_w = 8 * ns + 2 * pp;
-                p.halo_rows = (16 + 2 * pp) * p.halo_w;
+                p.halo_w = 8 * ns + halo_extra;
+                p.halo_rows = (16 + halo_extra) * p.halo_w;
                 p.halo_bytes = (p.halo_rows * 128 + 1023) & ~1023;
                 p.sa = env_na ? env_na : cand[ci][2];
                 const int left = 227 * 1024 - p.sa * p.halo_bytes - 8 * 1024;
@@ -677,6 +731,7 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
             cols = 32;
             while (cols < (persist ? 2 : 1) * p.ns * p.ks * L.cout) cols *= 2;
             p.tmem_cols = cols;
+            if (L.sub >= 0 && !persist) return fail(DSU_E_INVALID, "sub-pixel layers need the persistent halo kernel: " + L.name);
             if (persist) CUDA_TRY(launch_conv_halo_persist(p, st));
             else CUDA_TRY(launch_conv_halo(p, st));
         } else if (L.ric && ric_persist_mode != 0 && L.cout <= (ric_persist_mode == 2 ? 128 : 64)) {
@@ -918,7 +973,7 @@ double dsu_forward_flops(dsu_handle h, int32_t B, int32_t H, int32_t W) {
         if (mp == 0) {   // before finalize: derive from the plan
             double kk = 0;
             for (const SegDef& s : L.segs) kk += s.wn;
-            mp = kk * L.k * L.k * L.cout;
+            mp = L.sub >= 0 ? kk * 9.0 / 4.0 * L.cout : kk * L.k * L.k * L.cout;
         }
         macs += mp * static_cast<double>(H >> L.level_out) * (W >> L.level_out);
     }

@@ -214,3 +214,34 @@ def test_algorithmic_flop_model_matches_baseline_md():
         m += (2 if stage == 2 else 1) * 9 * f[5] * f[5] + 3 * f[5]
         return m
     assert macs(1) == 567552 and macs(2) == 1037056
+
+
+def test_subpixel_decomposition_of_upsample_conv_is_exact():
+    """The experimental DSU_SUBPIXEL plan (engine.cu compile_layer / conv_halo_persist_kernel<true>) replaces
+    nearest-x2 + 3x3 conv (models.py:180-192) by four 2x2 convolutions on the low-resolution tensor.  Same index
+    arithmetic restated with torch: class (py, px) writes out[2y+py, 2x+px], tap (a, b) reads in[y+a-1+py, x+b-1+px]
+    with the 3x3 weights that hit that source pixel summed - equal to the reference composition including the border."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 5, 7, 6, generator=g, dtype=torch.float64)
+    w = torch.randn(4, 5, 3, 3, generator=g, dtype=torch.float64)
+    want = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, padding=1)
+
+    def members(parity, tap):
+        if parity == 0:
+            return (0, 0) if tap == 0 else (1, 2)
+        return (0, 1) if tap == 0 else (2, 2)
+
+    got = torch.zeros_like(want)
+    for py in range(2):
+        for px in range(2):
+            wc = torch.zeros(4, 5, 2, 2, dtype=torch.float64)
+            for a in range(2):
+                for b in range(2):
+                    r0, r1 = members(py, a)
+                    c0, c1 = members(px, b)
+                    wc[:, :, a, b] = w[:, :, r0:r1 + 1, c0:c1 + 1].sum(dim=(2, 3))
+            # asymmetric zero padding: (1 - py) rows above, py below; (1 - px) columns left, px right
+            xp = F.pad(x, (1 - px, px, 1 - py, py))
+            got[:, :, py::2, px::2] = F.conv2d(xp, wc)
+    assert torch.allclose(got, want, rtol=0, atol=1e-12)
