@@ -273,7 +273,7 @@ cudaError_t launch_conv(const ConvParams& p, cudaStream_t stream) {
         return cudaErrorInvalidConfiguration;
     dim3 grid((p.Wout + kTileW - 1) / kTileW, (p.Hout + kTileH - 1) / kTileH, p.B);
     if (p.ric && p.exact) conv_umma_kernel<2><<<grid, kThreadsRic, conv_smem_bytes(p), stream>>>(p);
-    else if (p.ric == 2) conv_umma_kernel<3><<<grid, kThreadsRic, conv_smem_bytes(p), stream>>>(p);
+    else if (p.ric >= 2) conv_umma_kernel<3><<<grid, kThreadsRic, conv_smem_bytes(p), stream>>>(p);
     else if (p.ric) conv_umma_kernel<1><<<grid, kThreadsRic, conv_smem_bytes(p), stream>>>(p);
     else conv_umma_kernel<0><<<grid, kThreadsTap, conv_smem_bytes(p), stream>>>(p);
     return cudaGetLastError();

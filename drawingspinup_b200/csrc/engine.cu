@@ -642,6 +642,8 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
         p.stride = L.stride; p.ric = L.ric; p.exact = E->exact ? 1 : 0;
         // fp16 mode blends the RIC taps with packed half2 math unless DSU_RIC_FP32_BLEND=1 (p.ric == 2 selects it)
         if (L.ric && !E->exact && !std::getenv("DSU_RIC_FP32_BLEND")) p.ric = 2;
+        // experimental pixel-major producer of the persistent RIC kernel (same arithmetic; not yet validated on hardware)
+        if (p.ric == 2) { const char* ev = std::getenv("DSU_RIC_PIXEL_MAJOR"); if (ev && std::atoi(ev) != 0) p.ric = 3; }
         p.nchunks = L.nchunks; p.nblocks = L.nblocks; p.Cout = L.cout;
         p.b_bytes = L.cout * 128;
         p.kmask_full = L.kmask_full; p.kmask_last = L.kmask_last; p.kmask2_full = L.kmask2_full; p.kmask2_last = L.kmask2_last;

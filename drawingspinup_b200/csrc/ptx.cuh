@@ -112,6 +112,16 @@ __device__ __forceinline__ void st_global_256(void* ptr, const uint4& a, const u
                  : "memory");
 }
 
+// Read-only 128-bit global load under a predicate, zeros otherwise (no branch, no dependence on a dummy address).
+__device__ __forceinline__ uint4 ldg128_if(const void* ptr, bool ok) {
+    uint4 v;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\tmov.u32 %0, 0;\n\tmov.u32 %1, 0;\n\tmov.u32 %2, 0;\n\tmov.u32 %3, 0;\n\t"
+        "@p ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
+        : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+        : "l"(ptr), "r"(static_cast<uint32_t>(ok)));
+    return v;
+}
+
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle:
 // rows of 128 B (64 fp16), 8-row groups `sbo_bytes` apart.
