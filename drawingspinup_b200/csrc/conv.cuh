@@ -105,6 +105,7 @@ struct ConvParams {
     // the launch is a 2x2 convolution over the LOW-resolution source with asymmetric padding (pad_y, pad_x) whose output
     // pixel (oy, ox) of the Hout x Wout grid lands at (2*oy + sub_py, 2*ox + sub_px) of the (2*Hout) x (2*Wout) output buffer
     int sub, sub_py, sub_px, pad_y, pad_x;
+    int raw_choff;          // conv_ric_first.cu (experimental): first channel of the raw network input inside seg[0]
 };
 
 cudaError_t launch_conv(const ConvParams& p, cudaStream_t stream);
@@ -113,6 +114,7 @@ cudaError_t launch_conv_halo_persist(const ConvParams& p, cudaStream_t stream);
 cudaError_t launch_conv_ric_persist(const ConvParams& p, cudaStream_t stream);
 // first-layer kernel (conv_first.cu): reuses sa = halo buffers, ks = issuers, ns = accumulator sets, ksize / pad / halo_rows / halo_bytes
 cudaError_t launch_conv_first(const ConvParams& p, cudaStream_t stream);
+cudaError_t launch_conv_ric_first(const ConvParams& p, cudaStream_t stream);   // experimental, DSU_RIC_FIRST=1
 size_t conv_halo_smem_bytes(const ConvParams& p);
 size_t conv_smem_bytes(const ConvParams& p);
 

@@ -62,6 +62,7 @@ struct LayerDef {
     // same source pixel - exact including the zero border, 4 taps instead of 9 per output pixel.  k = 2 for such a layer and
     // wk = 3 is the kernel size of the stored weights; -1 = ordinary layer
     int sub = -1, wk = 0;
+    int raw_buf = -1, raw_choff = 0;   // expanded stage-1 conv0: where the un-expanded 8-channel input lives (conv_ric_first.cu)
     // compiled at finalize
     int nchunks = 0, nblocks = 0;
     uint32_t kmask_full = 0xF, kmask_last = 0xF, kmask2_full = 0, kmask2_last = 0;
@@ -190,6 +191,7 @@ int build_plan(dsu_engine* E) {
         if (ric) {   // sample the 9 taps of the 8-channel input once, then contract over 9 * cp channels
             E->steps.push_back(Step{2, -1, SK0, f[0], cp, EXP0});
             L.ric = 0; L.expanded = 1; L.segs = {{EXP0, 0, cp, 0, cin}};
+            L.raw_buf = SK0; L.raw_choff = f[0];
         }
         add(L);
     }
@@ -615,6 +617,9 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
     size_t step_idx = 0;
     int ric_persist_mode = 2;     // 0 never, 1 Cout <= 64, 2 all RIC layers (measured best: profiles/r01j)
     if (const char* ev = std::getenv("DSU_RIC_PERSIST")) ric_persist_mode = std::atoi(ev);
+    // experimental (not yet validated on hardware): stage-1 conv0 fused with its tap expansion (conv_ric_first.cu), fp16 mode
+    const char* rf_env = std::getenv("DSU_RIC_FIRST");
+    const bool ric_first = rf_env && std::atoi(rf_env) != 0 && !E->exact;
     int first_mode = 1;           // 0: conv0 of GeneratorJ stays in tap mode (conv_umma.cu), 1: conv_first.cu
     if (const char* ev = std::getenv("DSU_FIRST")) first_mode = std::atoi(ev);
     for (const Step& sp : E->steps) {
@@ -627,6 +632,7 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
             continue;
         }
         if (sp.type == 2) {
+            if (ric_first) continue;      // the consumer samples the taps itself
             CUDA_TRY(ric_expand(E->buf_hi[sp.src], E->buf_lo[sp.src], E->buf_C[sp.src], sp.src_choff, sp.C / 8, B, H, W,
                                 E->lv[0].lyx, E->lv[0].oct, E->buf_hi[sp.dst], E->buf_lo[sp.dst], st));
             continue;
@@ -679,6 +685,19 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
         if (L.final) {
             e.w12 = E->d_w12; e.b12 = E->d_b12; e.tanh_flag = E->cfg.tanh;
             e.y_nchw = y_dev; e.y_rgba = y_rgba; e.alpha_src = alpha_src; e.alpha_stride = alpha_stride;
+        }
+        if (L.expanded && ric_first && L.raw_buf >= 0 && L.nchunks == 2) {
+            p.seg[0].ptr = E->buf_hi[L.raw_buf];
+            p.seg[0].pitch = E->buf_C[L.raw_buf];
+            p.raw_choff = L.raw_choff;
+            p.ric_lyx = E->lv[0].lyx; p.ric_oct = E->lv[0].oct;
+            p.sa = 4;
+            p.ns = 4 * L.cout <= 512 ? 4 : 2;
+            cols = 32;
+            while (cols < p.ns * L.cout) cols *= 2;
+            p.tmem_cols = cols;
+            CUDA_TRY(launch_conv_ric_first(p, st));
+            continue;
         }
         if (L.halo) {
             // ns sub-tiles x ks K-split issuers (<= 4 issuing warps, <= 512 TMEM columns); shared memory:
