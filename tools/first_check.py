@@ -1,5 +1,6 @@
 """conv_first.cu vs the tap-mode kernel on GeneratorJ.conv0 (development aid, run under gpurun):
-activations of both paths on ragged shapes, then the per-layer timing of a 16 x 512 x 512 batch."""
+activations of both paths on ragged shapes, then conv0 timing of a 16 x 512 x 512 batch over the knobs
+DSU_FIRST (0 = tap mode), DSU_FIRST_KS (issuers), DSU_FIRST_SETS (accumulator sets)."""
 import os
 import sys
 
@@ -25,7 +26,7 @@ for (b, h, w) in [(1, 4, 4), (2, 8, 12), (1, 12, 4), (5, 20, 36), (1, 132, 68), 
         with torch.no_grad():
             y = m(x)
         torch.cuda.synchronize()
-        out[mode] = (y.cpu(), m.debug_buffer(0, 0, (b, h, w, 32)).float())
+        out[mode] = (y.cpu(), m.debug_buffer(0, 0, (b, h, w, 40)).float()[..., :32])
     dy = (out["0"][0] - out["1"][0]).abs().max().item()
     ds = (out["0"][1] - out["1"][1]).abs().max().item()
     print("shape %-14s conv0 |tap - first| %.2e  output %.2e  %s" % ((b, h, w), ds, dy, "OK" if ds < 2e-2 and dy < 5e-3 else "FAIL"), flush=True)
