@@ -157,3 +157,15 @@ def test_stylize_character_matches_oracle_chain(tmp_path):
             got2 = np.asarray(im)
         assert np.abs(got2.astype(int) - want2.astype(int)).max() <= 1
         assert (got2 != want2).mean() < 0.02
+
+
+def test_missing_edge_maps_and_empty_clips(tmp_path):
+    synth.write_character_tree(str(tmp_path), "u", {"a": 2}, 16, 16, state_dicts=({}, {}))
+    data_root = tmp_path / "u" / "mesh" / "blender_render"
+    os.makedirs(data_root / "empty" / "color")                      # a clip without frames is skipped
+    for f in os.listdir(data_root / "a" / "edge"):
+        os.remove(data_root / "a" / "edge" / f)
+    os.rmdir(data_root / "a" / "edge")
+    assert len(frame_io.FrameSet.load(str(data_root / "empty"), pin=False)) == 0
+    with pytest.raises(FileNotFoundError, match="edge"):             # stage 2 cannot run without run_render.py's edge maps
+        frame_io.stylize_character(str(tmp_path), "u", pipeline=_StandInPipeline())
