@@ -11,7 +11,7 @@ Public surface (mirrors ``3_style_translator/training/models.py`` for the infere
 """
 from .models import GeneratorJ, GeneratorJ_RIC, ric_offsets  # noqa: F401
 
-__all__ = ["GeneratorJ", "GeneratorJ_RIC", "ric_offsets", "install"]
+__all__ = ["GeneratorJ", "GeneratorJ_RIC", "ric_offsets", "install", "uninstall"]
 
 
 def install(models_module=None):
@@ -23,6 +23,26 @@ def install(models_module=None):
     if models_module is None:
         import importlib
         models_module = importlib.import_module("training.models")
+    # the reference classes call ``super(GeneratorJ_RIC, self).__init__()`` through the module-level NAME (models.py:204),
+    # so they cannot be constructed while the names are rebound: build reference models (in-process A/B checks) before
+    # install() or after uninstall().  The originals stay reachable as ``_dsu_original``.
+    if not hasattr(models_module, "_dsu_original"):
+        models_module._dsu_original = {"GeneratorJ_RIC": getattr(models_module, "GeneratorJ_RIC", None),
+                                       "GeneratorJ": getattr(models_module, "GeneratorJ", None)}
     models_module.GeneratorJ_RIC = GeneratorJ_RIC
     models_module.GeneratorJ = GeneratorJ
+    return models_module
+
+
+def uninstall(models_module=None):
+    """Undo :func:`install`: restore the reference's own ``GeneratorJ_RIC`` / ``GeneratorJ`` classes."""
+    if models_module is None:
+        import importlib
+        models_module = importlib.import_module("training.models")
+    orig = getattr(models_module, "_dsu_original", None)
+    if orig:
+        for name, cls in orig.items():
+            if cls is not None:
+                setattr(models_module, name, cls)
+        del models_module._dsu_original
     return models_module

@@ -38,8 +38,7 @@ __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.al
 
 }  // namespace
 
-// kMode: 1 = fp16 / fp32 blend, 2 = split fp16 hi|lo, 3 = fp16 / packed half2 blend,
-//        4 = as 3 with the pixel-major producer (experimental, DSU_RIC_PIXEL_MAJOR=1)
+// kMode: 1 = fp16 / fp32 blend, 2 = split fp16 hi|lo, 3 = fp16 / packed half2 blend
 template <int kMode>
 __global__ void __launch_bounds__(kRpThreads, 1)
 conv_ric_persist_kernel(const __grid_constant__ ConvParams p) {
@@ -107,8 +106,7 @@ conv_ric_persist_kernel(const __grid_constant__ ConvParams p) {
         for (int it = 0; it < my_tiles; ++it) {
             int n, ty0, tx0;
             tile_coords(it, n, ty0, tx0);
-            if constexpr (kMode == 4) ric_produce_px(p, smem + L.a0, bar_full_a, bar_empty_a, tid, n, ty0, tx0, it * p.nblocks);
-            else ric_produce<kMode == 2, kMode == 3>(p, smem + L.a0, bar_full_a, bar_empty_a, tid, n, ty0, tx0, it * p.nblocks);
+            ric_produce<kMode == 2, kMode == 3>(p, smem + L.a0, bar_full_a, bar_empty_a, tid, n, ty0, tx0, it * p.nblocks);
         }
     } else if (warp < 12) {
         // ======================================================== epilogue warpgroup (one warp per TMEM lane quadrant)
@@ -226,7 +224,6 @@ cudaError_t launch_conv_ric_persist(const ConvParams& p, cudaStream_t stream) {
         cudaError_t e = cudaFuncSetAttribute(conv_ric_persist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ric_persist_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ric_persist_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ric_persist_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
         attr_set[dev] = true;
@@ -238,7 +235,6 @@ cudaError_t launch_conv_ric_persist(const ConvParams& p, cudaStream_t stream) {
     const int ctas = tiles < sm_count[dev] ? tiles : sm_count[dev];
     const size_t smem = conv_ric_persist_smem_bytes(p);
     if (p.exact) conv_ric_persist_kernel<2><<<ctas, kRpThreads, smem, stream>>>(p);
-    else if (p.ric == 3) conv_ric_persist_kernel<4><<<ctas, kRpThreads, smem, stream>>>(p);
     else if (p.ric == 2) conv_ric_persist_kernel<3><<<ctas, kRpThreads, smem, stream>>>(p);
     else conv_ric_persist_kernel<1><<<ctas, kRpThreads, smem, stream>>>(p);
     return cudaGetLastError();

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -78,6 +79,51 @@ struct Step {
     int src, src_choff, C, dst;
 };
 
+// Development knobs: read ONCE from the environment (DSU_<NAME>) by dsu_create, adjustable per handle through
+// dsu_set_knob (tests / tools); 0 = "planner decides" for the sizing knobs.  Defaults are the measured best.
+struct Knobs {
+    int ric_persist = 2;      // 0 never, 1 Cout <= 64, 2 all RIC layers run the persistent kernel
+    int ric_first = 1;        // stage-1 conv0 fused with its tap expansion (conv_ric_first.cu; fp16 mode)
+    int ric_fp32_blend = 0;   // fp16 mode: blend the RIC taps in fp32 instead of packed half2
+    int ric_ks = 0;
+    int first = 1;            // GeneratorJ.conv0 in the im2col-free kernel (conv_first.cu); 0 = tap mode
+    int first_ks = 0, first_na = 0, first_sets = 0;
+    int halo_persist = 2, halo_ns = 0, halo_ks = 0, halo_na = 0, halo_sb = 0, halo_tps = 0;
+    int subpixel = 1;         // plan-time: stage-2 nearest-x2 + 3x3 as four 2x2 sub-pixel convolutions
+};
+struct KnobName { const char* name; int Knobs::*field; };
+const KnobName kKnobNames[] = {
+    {"ric_persist", &Knobs::ric_persist}, {"ric_first", &Knobs::ric_first}, {"ric_fp32_blend", &Knobs::ric_fp32_blend},
+    {"ric_ks", &Knobs::ric_ks}, {"first", &Knobs::first}, {"first_ks", &Knobs::first_ks}, {"first_na", &Knobs::first_na},
+    {"first_sets", &Knobs::first_sets}, {"halo_persist", &Knobs::halo_persist}, {"halo_ns", &Knobs::halo_ns},
+    {"halo_ks", &Knobs::halo_ks}, {"halo_na", &Knobs::halo_na}, {"halo_sb", &Knobs::halo_sb}, {"halo_tps", &Knobs::halo_tps},
+    {"subpixel", &Knobs::subpixel},
+};
+Knobs knobs_from_env() {
+    Knobs k;
+    for (const KnobName& kn : kKnobNames) {
+        std::string env = "DSU_";
+        for (const char* c = kn.name; *c; ++c) env += static_cast<char>(std::toupper(static_cast<unsigned char>(*c)));
+        if (const char* v = std::getenv(env.c_str())) k.*(kn.field) = std::atoi(v);
+    }
+    return k;
+}
+
+// Every C-ABI entry point runs on the handle's device and leaves the caller's current device as it found it.
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+        else if (err == cudaSuccess) prev = -1;          // nothing to restore
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define DEVICE_GUARD(h)                                                                        \
+    DeviceGuard guard__((h)->cfg.device);                                                      \
+    if (guard__.err != cudaSuccess) return fail(DSU_E_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(guard__.err))
+
 struct Level {
     int h = 0, w = 0;
     float2* lyx = nullptr;    // [h*w][8] bilinear fractions in rotated tap order
@@ -90,6 +136,7 @@ struct Level {
 
 struct dsu_engine {
     dsu_config cfg{};
+    Knobs knobs;
     int cin_pad = 8;
     bool exact = false, finalized = false;
     std::map<std::string, std::vector<int64_t>> expected;
@@ -224,10 +271,9 @@ int build_plan(dsu_engine* E) {
         Bl.out_buf = TT; Bl.out_relu = (i + 1 < c.resnet_blocks) ? 1 : 0;
         add(Bl);
     }
-    // plain (stage-2) up-convolutions can run as four sub-pixel 2x2 convolutions on the low-resolution source (2.25x fewer
-    // MACs); experimental until validated on hardware, so only with DSU_SUBPIXEL=1 in the environment of dsu_create
-    const char* sub_env = std::getenv("DSU_SUBPIXEL");
-    const bool subpixel = !ric && sub_env && std::atoi(sub_env) != 0;
+    // plain (stage-2) up-convolutions run as four sub-pixel 2x2 convolutions on the low-resolution source (2.25x fewer
+    // MACs; validated on hardware in round 2, profiles/r02a_experimental.log); DSU_SUBPIXEL=0 at dsu_create restores the 3x3 form
+    const bool subpixel = !ric && E->knobs.subpixel != 0;
     auto add_up = [&](LayerDef L) {
         if (!subpixel) { L.up = 1; add(L); return; }
         const std::string base = L.name;
@@ -615,13 +661,15 @@ void pick_stages(bool ric, int b_bytes, int* sa, int* sb) {
 int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgba, const uint8_t* alpha_src,
                 int alpha_stride, cudaStream_t st, std::vector<cudaEvent_t>* evs = nullptr) {
     size_t step_idx = 0;
-    int ric_persist_mode = 2;     // 0 never, 1 Cout <= 64, 2 all RIC layers (measured best: profiles/r01j)
-    if (const char* ev = std::getenv("DSU_RIC_PERSIST")) ric_persist_mode = std::atoi(ev);
-    // experimental (not yet validated on hardware): stage-1 conv0 fused with its tap expansion (conv_ric_first.cu), fp16 mode
-    const char* rf_env = std::getenv("DSU_RIC_FIRST");
-    const bool ric_first = rf_env && std::atoi(rf_env) != 0 && !E->exact;
-    int first_mode = 1;           // 0: conv0 of GeneratorJ stays in tap mode (conv_umma.cu), 1: conv_first.cu
-    if (const char* ev = std::getenv("DSU_FIRST")) first_mode = std::atoi(ev);
+    const Knobs& K = E->knobs;
+    const int ric_persist_mode = K.ric_persist;
+    // stage-1 conv0 fused with its tap expansion (conv_ric_first.cu): fp16 mode, one 8-channel input group (2 weight chunks).
+    // ONE predicate decides both "skip the ric_expand step" and "launch the fused kernel" (a conv0 with 9..16 input channels
+    // keeps the expansion buffer and the halo kernel).
+    bool use_ric_first = false;
+    for (const LayerDef& L : E->layers)
+        if (L.expanded) use_ric_first = K.ric_first != 0 && !E->exact && L.raw_buf >= 0 && L.nchunks == 2;
+    const int first_mode = K.first;
     for (const Step& sp : E->steps) {
         if (evs) CUDA_TRY(cudaEventRecord((*evs)[step_idx], st));
         ++step_idx;
@@ -632,7 +680,7 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
             continue;
         }
         if (sp.type == 2) {
-            if (ric_first) continue;      // the consumer samples the taps itself
+            if (use_ric_first) continue;      // the consumer samples the taps itself
             CUDA_TRY(ric_expand(E->buf_hi[sp.src], E->buf_lo[sp.src], E->buf_C[sp.src], sp.src_choff, sp.C / 8, B, H, W,
                                 E->lv[0].lyx, E->lv[0].oct, E->buf_hi[sp.dst], E->buf_lo[sp.dst], st));
             continue;
@@ -647,9 +695,7 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
         p.up = L.up; p.Hv = p.Hin << L.up; p.Wv = p.Win << L.up;
         p.stride = L.stride; p.ric = L.ric; p.exact = E->exact ? 1 : 0;
         // fp16 mode blends the RIC taps with packed half2 math unless DSU_RIC_FP32_BLEND=1 (p.ric == 2 selects it)
-        if (L.ric && !E->exact && !std::getenv("DSU_RIC_FP32_BLEND")) p.ric = 2;
-        // experimental pixel-major producer of the persistent RIC kernel (same arithmetic; not yet validated on hardware)
-        if (p.ric == 2) { const char* ev = std::getenv("DSU_RIC_PIXEL_MAJOR"); if (ev && std::atoi(ev) != 0) p.ric = 3; }
+        if (L.ric && !E->exact && !K.ric_fp32_blend) p.ric = 2;
         p.nchunks = L.nchunks; p.nblocks = L.nblocks; p.Cout = L.cout;
         p.b_bytes = L.cout * 128;
         p.kmask_full = L.kmask_full; p.kmask_last = L.kmask_last; p.kmask2_full = L.kmask2_full; p.kmask2_last = L.kmask2_last;
@@ -657,7 +703,7 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
         p.ks = 1;
         if (L.ric) {   // K-split issuers: each needs a private weight ring of >= 2 stages and a TMEM accumulator
             p.ks = std::max(1, std::min(kIssuersRic, std::min(p.sb / 2, 512 / L.cout)));
-            if (const char* ev = std::getenv("DSU_RIC_KS")) p.ks = std::max(1, std::min(p.ks, std::atoi(ev)));
+            if (K.ric_ks > 0) p.ks = std::max(1, std::min(p.ks, K.ric_ks));
             p.sb = (p.sb / p.ks) * p.ks;
         }
         int cols = 32;
@@ -686,7 +732,7 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
             e.w12 = E->d_w12; e.b12 = E->d_b12; e.tanh_flag = E->cfg.tanh;
             e.y_nchw = y_dev; e.y_rgba = y_rgba; e.alpha_src = alpha_src; e.alpha_stride = alpha_stride;
         }
-        if (L.expanded && ric_first && L.raw_buf >= 0 && L.nchunks == 2) {
+        if (L.expanded && use_ric_first) {
             p.seg[0].ptr = E->buf_hi[L.raw_buf];
             p.seg[0].pitch = E->buf_C[L.raw_buf];
             p.raw_choff = L.raw_choff;
@@ -715,11 +761,9 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
             static const int cand3[][3] = {{4, 1, 2}, {2, 2, 2}, {2, 1, 2}, {1, 2, 2}, {1, 1, 2}};
             static const int cand7[][3] = {{4, 1, 1}, {2, 2, 2}, {2, 1, 2}, {1, 2, 2}, {1, 1, 2}};
             const int (*cand)[3] = kk <= 3 ? cand3 : cand7;
-            int env_ns = 0, env_ks = 0, env_na = 0, persist_mode = 2;   // 0 never, 1 when the chosen config allows, 2 prefer (measured best)
-            if (const char* ev = std::getenv("DSU_HALO_PERSIST")) persist_mode = std::atoi(ev);
-            if (const char* ev = std::getenv("DSU_HALO_NS")) env_ns = std::max(1, std::min(4, std::atoi(ev)));
-            if (const char* ev = std::getenv("DSU_HALO_KS")) env_ks = std::max(1, std::min(4, std::atoi(ev)));
-            if (const char* ev = std::getenv("DSU_HALO_NA")) env_na = std::max(1, std::min(3, std::atoi(ev)));
+            const int persist_mode = K.halo_persist;   // 0 never, 1 when the chosen config allows, 2 prefer (measured best)
+            const int env_ns = K.halo_ns > 0 ? std::min(4, K.halo_ns) : 0, env_ks = K.halo_ks > 0 ? std::min(4, K.halo_ks) : 0;
+            const int env_na = K.halo_na > 0 ? std::min(3, K.halo_na) : 0;
             bool found = false;
             for (int ci = 0; ci < 5 && !found; ++ci) {
                 const int ns = env_ns ? env_ns : cand[ci][0], ks = env_ks ? env_ks : cand[ci][1];
@@ -732,7 +776,7 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
                 p.sa = env_na ? env_na : cand[ci][2];
                 const int left = 227 * 1024 - p.sa * p.halo_bytes - 8 * 1024;
                 p.sb = left < 0 ? 0 : std::min(kMaxStagesB, left / p.b_bytes);
-                if (const char* ev = std::getenv("DSU_HALO_SB")) p.sb = std::max(2, std::min(p.sb, std::atoi(ev)));
+                if (K.halo_sb > 0) p.sb = std::max(2, std::min(p.sb, K.halo_sb));
                 p.sb = (p.sb / ks) * ks;
                 found = p.sb / ks >= 3 || (ci == 4 && p.sb / ks >= 2);
             }
@@ -742,7 +786,7 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
             p.tps = 1;
             if (persist) {   // taps per weight stage: up to 3 while the ring stays >= 3 stages deep (per K-split group)
                 int tps = 3;
-                if (const char* ev = std::getenv("DSU_HALO_TPS")) tps = std::max(1, std::min(4, std::atoi(ev)));
+                if (K.halo_tps > 0) tps = std::max(1, std::min(4, K.halo_tps));
                 const int left = 227 * 1024 - p.sa * p.halo_bytes - 8 * 1024;
                 while (tps > 1 && (left / (tps * p.b_bytes)) / p.ks < 3) --tps;
                 p.tps = tps;
@@ -773,13 +817,13 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
                 p.halo_bytes = p.halo_rows * 16 * 16;
                 const int ks_max = std::min(4, std::min(L.k, 256 / L.cout));
                 p.ks = std::min(2, ks_max);
-                if (const char* ev = std::getenv("DSU_FIRST_KS")) p.ks = std::max(1, std::min(ks_max, std::atoi(ev)));
+                if (K.first_ks > 0) p.ks = std::max(1, std::min(ks_max, K.first_ks));
                 const int left = 227 * 1024 - L.nchunks * p.b_bytes - 8 * 1024;
                 p.sa = std::min(4, left / p.halo_bytes);
-                if (const char* ev = std::getenv("DSU_FIRST_NA")) p.sa = std::max(2, std::min(6, std::min(left / p.halo_bytes, std::atoi(ev))));
+                if (K.first_na > 0) p.sa = std::max(2, std::min(6, std::min(left / p.halo_bytes, K.first_na)));
                 if (p.ks >= 1 && p.sa >= 2) {
                     p.ns = 4 * p.ks * L.cout <= 512 ? 4 : 2;          // accumulator sets in TMEM
-                    if (const char* ev = std::getenv("DSU_FIRST_SETS")) p.ns = (std::atoi(ev) >= 4 && p.ns == 4) ? 4 : 2;
+                    if (K.first_sets > 0) p.ns = (K.first_sets >= 4 && p.ns == 4) ? 4 : 2;
                     cols = 32;
                     while (cols < p.ns * p.ks * L.cout) cols *= 2;
                     p.tmem_cols = cols;
@@ -836,9 +880,9 @@ int dsu_create(const dsu_config* cfg, dsu_handle* out) {
     CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
     if (prop.major != 10)
         return fail(DSU_E_INVALID, std::string("device '") + prop.name + "' is not sm_100 (tcgen05 kernels only, no fallback path)");
-    CUDA_TRY(cudaSetDevice(cfg->device));
     dsu_engine* E = new dsu_engine();
     E->cfg = *cfg;
+    E->knobs = knobs_from_env();
     E->cin_pad = (cfg->input_channels + 7) / 8 * 8;
     E->exact = cfg->precision == DSU_PREC_FP16X3;
     int rc = build_plan(E);
@@ -849,7 +893,7 @@ int dsu_create(const dsu_config* cfg, dsu_handle* out) {
 
 void dsu_destroy(dsu_handle h) {
     if (!h) return;
-    cudaSetDevice(h->cfg.device);
+    DeviceGuard guard(h->cfg.device);
     for (LayerDef& L : h->layers) {
         cudaFree(L.d_slots); cudaFree(L.d_wpack);
         cudaFree(L.d_scale); cudaFree(L.d_shift); cudaFree(L.d_scale2); cudaFree(L.d_shift2);
@@ -880,7 +924,7 @@ int dsu_load_weights(dsu_handle h, const char* key, const void* data, const int6
     std::vector<float>& dst = h->w[key];
     dst.resize(n);
     if (location == 1) {
-        CUDA_TRY(cudaSetDevice(h->cfg.device));
+        DEVICE_GUARD(h);
         CUDA_TRY(cudaMemcpy(dst.data(), data, n * sizeof(float), cudaMemcpyDeviceToHost));
     } else {
         std::memcpy(dst.data(), data, n * sizeof(float));
@@ -894,7 +938,7 @@ int dsu_finalize(dsu_handle h, void* stream) {
     if (!h) return fail(DSU_E_INVALID, "null handle");
     for (const std::string& k : h->expected_order)
         if (!h->loaded.count(k)) return fail(DSU_E_STATE, "missing key in state_dict: " + k);
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    DEVICE_GUARD(h);
     for (LayerDef& L : h->layers) {
         int rc = compile_layer(h, L);
         if (rc) return rc;
@@ -905,6 +949,18 @@ int dsu_finalize(dsu_handle h, void* stream) {
     if ((rc = upload(&h->d_b12, h->w.at(p12 + ".bias")))) return rc;
     h->finalized = true;
     return DSU_OK;
+}
+
+int dsu_set_knob(dsu_handle h, const char* name, int32_t value) {
+    if (!h || !name) return fail(DSU_E_INVALID, "null argument");
+    for (const KnobName& kn : kKnobNames)
+        if (std::strcmp(kn.name, name) == 0) {
+            if (kn.field == &Knobs::subpixel && h->knobs.subpixel != value)
+                return fail(DSU_E_STATE, "'subpixel' shapes the launch plan: set DSU_SUBPIXEL in the environment before dsu_create");
+            h->knobs.*(kn.field) = value;
+            return DSU_OK;
+        }
+    return fail(DSU_E_INVALID, std::string("unknown knob: ") + name);
 }
 
 int dsu_set_ric_offsets(dsu_handle h, int32_t height, int32_t width, const float* offsets_host) {
@@ -919,7 +975,7 @@ int dsu_forward(dsu_handle h, const float* x_dev, int32_t B, int32_t H, int32_t 
     int rc = check_ready(h);
     if (rc) return rc;
     if (!x_dev || !y_dev) return fail(DSU_E_INVALID, "null tensor pointer");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    DEVICE_GUARD(h);
     if ((rc = ensure_shape(h, B, H, W))) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CUDA_TRY(ingest_f32(x_dev, B, h->cfg.input_channels, h->cin_pad, H, W, h->buf_hi[SK0], h->buf_lo[SK0],
@@ -934,7 +990,7 @@ int dsu_forward_u8(dsu_handle h, const uint8_t* color_dev, const uint8_t* pos_de
     if (!color_dev || !pos_dev || !out_rgba_dev) return fail(DSU_E_INVALID, "null frame pointer");
     if (h->cfg.input_channels != 6)
         return fail(DSU_E_INVALID, "the fused uint8 frame path needs input_channels == 6 (RGB + mask + posXY, test_stage1.py:33-39)");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    DEVICE_GUARD(h);
     if ((rc = ensure_shape(h, B, H, W))) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CUDA_TRY(ingest_u8(color_dev, pos_dev, edge_dev, B, H, W, h->buf_hi[SK0], h->buf_lo[SK0], h->buf_C[SK0],
@@ -947,7 +1003,7 @@ int dsu_forward_u8_host(dsu_handle h, const uint8_t* color_host, const uint8_t* 
     int rc = check_ready(h);
     if (rc) return rc;
     if (!color_host || !pos_host || !out_rgba_host) return fail(DSU_E_INVALID, "null frame pointer");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    DEVICE_GUARD(h);
     const size_t np = static_cast<size_t>(B) * H * W;
     if (np * 4 > h->io_cap) {
         cudaFree(h->io_color); cudaFree(h->io_pos); cudaFree(h->io_edge); cudaFree(h->io_out);
@@ -1007,11 +1063,16 @@ int dsu_profile_forward(dsu_handle h, int32_t B, int32_t H, int32_t W, int32_t r
     int rc = check_ready(h);
     if (rc) return rc;
     if (!ms_out || !flops_out || reps <= 0) return fail(DSU_E_INVALID, "bad argument");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    DEVICE_GUARD(h);
     if ((rc = ensure_shape(h, B, H, W))) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t n = h->steps.size();
-    std::vector<cudaEvent_t> evs(n + 1);
+    struct Events {                                   // destroyed on every exit path
+        std::vector<cudaEvent_t> v;
+        ~Events() { for (cudaEvent_t e : v) if (e) cudaEventDestroy(e); }
+    } events;
+    events.v.assign(n + 1, nullptr);
+    std::vector<cudaEvent_t>& evs = events.v;
     for (auto& e : evs) CUDA_TRY(cudaEventCreate(&e));
     std::vector<double> acc(n, 0.0);
     for (int r = 0; r < reps; ++r) {
@@ -1023,7 +1084,6 @@ int dsu_profile_forward(dsu_handle h, int32_t B, int32_t H, int32_t W, int32_t r
             acc[i] += ms;
         }
     }
-    for (auto& e : evs) cudaEventDestroy(e);
     for (size_t i = 0; i < n && i < static_cast<size_t>(capacity); ++i) {
         ms_out[i] = acc[i] / reps;
         const Step& sp = h->steps[i];
@@ -1075,7 +1135,7 @@ int dsu_pos2edge(const uint8_t* pos_dev, int32_t B, int32_t H, int32_t W, uint8_
 
 int dsu_debug_read(dsu_handle h, int32_t buffer, int32_t plane, void* dst_host, size_t bytes) {
     if (!h || !dst_host) return fail(DSU_E_INVALID, "null argument");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    DEVICE_GUARD(h);
     CUDA_TRY(cudaDeviceSynchronize());
     const void* src = nullptr;
     size_t have = 0;

@@ -216,120 +216,4 @@ __device__ __forceinline__ void ric_produce(const ConvParams& p, uint8_t* a_smem
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------------
-// Pixel-major producer (fp16 mode, packed half2 blend; experimental, DSU_RIC_PIXEL_MAJOR=1 -> conv_ric_persist_kernel<4>).
-//
-// ric_produce() above maps a thread to (4 pixels, 1 slot): everything that depends only on the PIXEL - the 64-byte stencil
-// entry, the octant, the 4 broadcast weights of each of the 8 taps, the 9 neighbour offsets with their border tests, the
-// A-buffer address of each rotated tap - is recomputed for every (pixel, slot) item of every 64-channel block, ~80 of the
-// ~230 instructions of an item (profiles/r01n_ric_persist_upconv1.ncu-rep: the producers are issue-bound).  Here a thread owns
-// ONE pixel of the tile and 4 of its 8 slots (lane pair (2r, 2r+1) shares pixel r; item u covers slot 2u + q so that the
-// pair reads one full 32-byte sector per neighbour), keeps the per-pixel state in registers for the whole tile and only
-// runs load -> blend -> store per item.  Items are software-pipelined across block boundaries.  Same arithmetic, same
-// operation order and same barrier protocol as ric_produce<false, true>, so the A operand is bit-identical.
-__device__ __forceinline__ void ric_produce_px(const ConvParams& p, uint8_t* a_smem, uint32_t bar_full_a, uint32_t bar_empty_a,
-                                               int tid, int n, int ty0, int tx0, int g0) {
-    const int r = tid >> 1, q = tid & 1, swz = r & 7;
-    const int oy = ty0 + (r >> 4), ox = tx0 + (r & 15);
-    const bool live = oy < p.Hout && ox < p.Wout;
-    const size_t frame_in = static_cast<size_t>(n) * p.Hin * p.Win;
-
-    // ---- per-pixel state, loaded once per tile
-    __half2 w[8][4];                 // the 4 bilinear weights of rotated tap m, each broadcast to both halves
-    int oct = 0;
-    {
-        uint4 t[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-        if (live) {
-            const size_t e = static_cast<size_t>(oy) * p.Wout + ox;
-            const uint4* tp = reinterpret_cast<const uint4*>(p.ric_wh + e * 8);      // 8 taps x {w00,w01 | w10,w11} fp16
-#pragma unroll
-            for (int i = 0; i < 4; ++i) t[i] = __ldg(tp + i);
-            oct = __ldg(p.ric_oct + e);
-        }
-#pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            const uint32_t a = (m & 1) ? t[m >> 1].z : t[m >> 1].x, b = (m & 1) ? t[m >> 1].w : t[m >> 1].y;
-            const __half2 wa = *reinterpret_cast<const __half2*>(&a), wb = *reinterpret_cast<const __half2*>(&b);
-            w[m][0] = __low2half2(wa); w[m][1] = __high2half2(wa); w[m][2] = __low2half2(wb); w[m][3] = __high2half2(wb);
-        }
-    }
-    int off[9];                      // source pixel of each 3x3 neighbour (fused nearest-x2: >> up)
-    uint32_t okmask = 0;             // bit k: neighbour k lies inside the image (else it contributes zero)
-#pragma unroll
-    for (int rr = 0; rr < 3; ++rr) {
-        const int vy = oy + rr - 1;
-        const bool oky = live && static_cast<unsigned>(vy) < static_cast<unsigned>(p.Hv);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const int vx = ox + c - 1;
-            const bool ok = oky && static_cast<unsigned>(vx) < static_cast<unsigned>(p.Wv);
-            off[rr * 3 + c] = ok ? (vy >> p.up) * p.Win + (vx >> p.up) : 0;
-            okmask |= static_cast<uint32_t>(ok) << (rr * 3 + c);
-        }
-    }
-    const uint32_t row_s = smem_u32(a_smem) + static_cast<uint32_t>(r) * 128u;
-    uint32_t tapaddr[8];             // shared-memory row of this pixel in the A buffer (raster tap, centre skipped) of rotated tap m
-#pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        const int kq = (m - oct) & 7;
-        tapaddr[m] = row_s + static_cast<uint32_t>(kq + (kq >> 2)) * kABytes;
-    }
-    const uint32_t centre = row_s + 4u * kABytes;
-    auto sts128 = [](uint32_t addr, const uint4& v) {
-        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-    };
-
-    auto load_item = [&](int b, int u, uint4 (&nb)[9]) {
-        const Slot sl = p.slots[b * 8 + 2 * u + q];
-        const Seg sg = p.seg[sl.seg];
-        const char* fb = reinterpret_cast<const char*>(sg.ptr + sl.choff + frame_in * sg.pitch);
-        const uint32_t pitch_b = static_cast<uint32_t>(sg.pitch) * 2u;               // bytes per pixel
-        const uint32_t mask = sl.valid ? okmask : 0u;
-#pragma unroll
-        for (int k = 0; k < 9; ++k)     // base + u32 x u32 -> one IMAD.WIDE.U32, predicated load
-            nb[k] = ldg128_if(fb + static_cast<uint64_t>(static_cast<uint32_t>(off[k])) * pitch_b, (mask >> k) & 1u);
-    };
-    auto blend_item = [&](int b, int u, const uint4 (&nb)[9]) {
-        if (u == 0 && g0 + b > 0) {     // the previous block's MMAs must have drained the 9 tap buffers (all lanes poll)
-#pragma unroll 1
-            for (int t = 0; t < 9; ++t) mbar_wait(bar_empty_a + 8 * t, (g0 + b - 1) & 1);
-        }
-        const uint32_t slot_off = static_cast<uint32_t>((2 * u + q) ^ swz) << 4;
-        sts128(centre + slot_off, nb[4]);                                            // centre tap = the pixel itself
-#pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            const int r0 = ric_r0(m), c0 = ric_c0(m);
-            const __half2* n00 = reinterpret_cast<const __half2*>(&nb[r0 * 3 + c0]);
-            const __half2* n01 = reinterpret_cast<const __half2*>(&nb[r0 * 3 + c0 + 1]);
-            const __half2* n10 = reinterpret_cast<const __half2*>(&nb[(r0 + 1) * 3 + c0]);
-            const __half2* n11 = reinterpret_cast<const __half2*>(&nb[(r0 + 1) * 3 + c0 + 1]);
-            uint4 v;
-            __half2* o = reinterpret_cast<__half2*>(&v);
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-                o[c] = __hfma2(w[m][3], n11[c], __hfma2(w[m][2], n10[c], __hfma2(w[m][1], n01[c], __hmul2(w[m][0], n00[c]))));
-            sts128(tapaddr[m] + slot_off, v);
-        }
-    };
-
-    uint4 nbA[9], nbB[9];
-    load_item(0, 0, nbA);
-    for (int b = 0; b < p.nblocks; ++b) {
-        load_item(b, 1, nbB);
-        blend_item(b, 0, nbA);
-        load_item(b, 2, nbA);
-        blend_item(b, 1, nbB);
-        load_item(b, 3, nbB);
-        blend_item(b, 2, nbA);
-        if (b + 1 < p.nblocks) load_item(b + 1, 0, nbA);     // prefetch across the block boundary
-        blend_item(b, 3, nbB);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if ((tid & 31) == 0) {
-#pragma unroll 1
-            for (int t = 0; t < 9; ++t) mbar_arrive(bar_full_a + 8 * t);
-        }
-    }
-}
-
 }  // namespace dsu

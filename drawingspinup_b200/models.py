@@ -207,10 +207,18 @@ class _Generator(nn.Module):
     def _prepare_shape(self, h: int, w: int):
         pass
 
+    def set_knob(self, name: str, value: int, device=None):
+        """Development / test hook (C ABI ``dsu_set_knob``): kernel-selection knob of this module's engine handle."""
+        dev = torch.device(device) if device is not None else (
+            torch.device("cuda", self._handle_dev) if self._handle_dev is not None else next(self.parameters()).device)
+        capi.check(capi.lib().dsu_set_knob(self._engine(dev), name.encode(), int(value)), "dsu_set_knob(%s)" % name)
+
     def _check_mode(self):
-        if self.training and torch.is_grad_enabled():
-            raise RuntimeError("drawingspinup_b200 generators are inference-only: call .eval() and/or run under "
-                               "torch.no_grad() (training, trainers.py:90-108, is out of scope)")
+        # train() mode would mean batch-statistics BatchNorm in the reference (even under no_grad); the engine only
+        # implements the eval-mode affine, so a module left in train() fails loudly instead of diverging silently
+        if self.training:
+            raise RuntimeError("drawingspinup_b200 generators are inference-only: call .eval() first (the reference scripts do, "
+                               "test_stage1.py:48); training, trainers.py:90-108, is out of scope")
 
     # ------------------------------------------------------------------ reference API
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -277,6 +285,10 @@ class _Generator(nn.Module):
         """2 x live MACs of one forward (the dead stage-1 smoother conv excluded)."""
         dev = torch.device("cuda", self._handle_dev) if self._handle_dev is not None else next(self.parameters()).device
         return float(capi.lib().dsu_forward_flops(self._engine(dev), b, h, w))
+
+    def workspace_bytes(self, b: int, h: int, w: int) -> int:
+        dev = torch.device("cuda", self._handle_dev) if self._handle_dev is not None else next(self.parameters()).device
+        return int(capi.lib().dsu_workspace_bytes(self._engine(dev), b, h, w))
 
     def kernel_launches(self, b: int, h: int, w: int) -> int:
         dev = torch.device("cuda", self._handle_dev) if self._handle_dev is not None else next(self.parameters()).device

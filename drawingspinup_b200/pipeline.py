@@ -77,11 +77,14 @@ class StylizationPipeline:
         self.batch = int(batch)
         a = dict(DEFAULT_ARGS if args is None else args)
         self.g1 = GeneratorJ_RIC(precision=precision, **a)
-        self.g2 = GeneratorJ(precision=precision, **a)
         self.g1.load_state_dict(sd_stage1)
-        self.g2.load_state_dict(sd_stage2)
         self.g1 = self.g1.to(self.device).eval()
-        self.g2 = self.g2.to(self.device).eval()
+        # sd_stage2 = None: stage 1 only (test_stage1.py alone; BASELINE configs[4]) - run() then returns the stage-1 RGBA
+        self.g2 = None
+        if sd_stage2 is not None:
+            self.g2 = GeneratorJ(precision=precision, **a)
+            self.g2.load_state_dict(sd_stage2)
+            self.g2 = self.g2.to(self.device).eval()
 
     @torch.no_grad()
     def run(self, color: torch.Tensor, pos: torch.Tensor, edge: torch.Tensor, keep_stage1: bool = False):
@@ -93,7 +96,7 @@ class StylizationPipeline:
         for lo in range(0, n, self.batch):
             hi = min(n, lo + self.batch)
             r1 = self.g1.forward_frames(color[lo:hi], pos[lo:hi], None)
-            out[lo:hi] = self.g2.forward_frames(r1, pos[lo:hi], edge[lo:hi])
+            out[lo:hi] = self.g2.forward_frames(r1, pos[lo:hi], edge[lo:hi]) if self.g2 is not None else r1
             if mid is not None:
                 mid[lo:hi] = r1
         return (out, mid) if keep_stage1 else out
@@ -134,7 +137,7 @@ class StylizationPipeline:
             nxt = upload(spans[i + 1]) if i + 1 < len(spans) else None
             main.wait_event(ev)
             r1 = self.g1.forward_frames(c, p, None)
-            r2 = self.g2.forward_frames(r1, p, e)
+            r2 = self.g2.forward_frames(r1, p, e) if self.g2 is not None else r1
             done = torch.cuda.Event()
             done.record(main)
             with torch.cuda.stream(cs):
@@ -153,7 +156,11 @@ class StylizationPipeline:
         return mid if keep_stage1 else out
 
     def flops_per_frame(self, h: int, w: int) -> float:
-        return self.g1.algorithmic_flops(1, h, w) + self.g2.algorithmic_flops(1, h, w)
+        return self.g1.algorithmic_flops(1, h, w) + (self.g2.algorithmic_flops(1, h, w) if self.g2 is not None else 0.0)
 
     def launches_per_batch(self, b: int, h: int, w: int) -> int:
-        return self.g1.kernel_launches(b, h, w) + self.g2.kernel_launches(b, h, w)
+        return self.g1.kernel_launches(b, h, w) + (self.g2.kernel_launches(b, h, w) if self.g2 is not None else 0)
+
+    def workspace_bytes(self, b: int, h: int, w: int) -> int:
+        """HBM the engine handles hold for a ``b``-frame batch of this size (activations, residual stream, RIC stencils)."""
+        return self.g1.workspace_bytes(b, h, w) + (self.g2.workspace_bytes(b, h, w) if self.g2 is not None else 0)

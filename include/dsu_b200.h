@@ -79,6 +79,11 @@ int dsu_loaded_keys(dsu_handle h);
  * tensor-core tiles, upload.  Requires every expected key (strict=True semantics). */
 int dsu_finalize(dsu_handle h, void* stream);
 
+/* Development / test hook, no counterpart in the reference: kernel-selection knobs of this handle ("first", "ric_first",
+ * "ric_persist", "halo_ns", ... - engine.cu Knobs).  Their defaults are read once from the environment (DSU_<NAME>) by
+ * dsu_create; "subpixel" shapes the launch plan and can only be set through the environment (DSU_E_STATE otherwise). */
+int dsu_set_knob(dsu_handle h, const char* name, int32_t value);
+
 /* generate_coordinates (models.py:551-604) is data independent; by default the engine derives the
  * per-level bilinear stencil from its own float math.  A host binding that wants the offsets
  * bit-identical to torch's (the Python mirror does) supplies them: offsets_host = fp32 [18, h, w]. */

@@ -2,8 +2,10 @@
 
 Restates, function by function, what ``/root/reference/3_style_translator`` computes
 for per-frame stylization inference.  Written from the reference's behaviour, not
-copied from it; every function cites the file:line it follows.  fp32 torch-CPU /
-numpy arithmetic, no CUDA, no dependency on ``/root/reference`` at run time.
+copied from it; every function cites the file:line it follows.  fp32 torch /
+numpy arithmetic on whatever device the input tensors live on (the CPU in the tests and the
+CPU baseline; ``cuda`` only for bench.py's reference-on-GPU comparison arm, where torch's own
+cuDNN / torchvision CUDA kernels play the reference), no dependency on ``/root/reference`` at run time.
 
 Pinning status: the reference ships NO golden vectors / KATs for this path
 ("parity unpinned" by the reference's own tests).  This port
@@ -105,12 +107,13 @@ def deform_conv3x3_port(x: torch.Tensor, offsets: torch.Tensor, weight: torch.Te
     batch-independent offset field ``offsets[18,h,w]`` (call sites models.py:302-351).
     Pure torch gather + matmul; no bias, no mask, stride 1, dilation 1, groups 1."""
     b, c, h, w = x.shape
-    idx, wgt = bilinear_taps(offsets, h, w)
+    idx, wgt = bilinear_taps(offsets.cpu(), h, w)
+    idx, wgt = idx.to(x.device), wgt.to(x.device)
     flat = x.reshape(b, c, h * w)
-    out = torch.zeros(b, weight.shape[0], h, w, dtype=x.dtype)
+    out = torch.zeros(b, weight.shape[0], h, w, dtype=x.dtype, device=x.device)
     for tap in range(9):
         i, j = divmod(tap, 3)
-        samp = torch.zeros(b, c, h * w, dtype=x.dtype)
+        samp = torch.zeros(b, c, h * w, dtype=x.dtype, device=x.device)
         for cn in range(4):
             samp = samp + flat[:, :, idx[tap, cn].reshape(-1)] * wgt[tap, cn].reshape(1, 1, -1)
         out = out + torch.einsum("oc,bcp->bop", weight[:, :, i, j], samp).reshape(b, -1, h, w)
@@ -201,9 +204,11 @@ def generator_j_ric_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, cfg: O
     cfg = cfg or default_config(1)
     rec = (lambda k, v: taps.__setitem__(k, v.clone())) if taps is not None else (lambda k, v: None)
     h, w = x.shape[2], x.shape[3]
-    c0 = ric_offsets(h, w)
-    c1 = ric_offsets(int(h / 2), int(w / 2))
-    c2 = ric_offsets(int(h / 4), int(w / 4))
+    # the field is computed on the CPU (bit-identical on every host) and moved to x's device: the reference does the same
+    # (CPU torch ops, then .cuda(), models.py:551-602); tests run this port on the CPU, bench.py's reference-on-GPU arm on cuda
+    c0 = ric_offsets(h, w).to(x.device)
+    c1 = ric_offsets(int(h / 2), int(w / 2)).to(x.device)
+    c2 = ric_offsets(int(h / 4), int(w / 4)).to(x.device)
     dc = lambda a, off, key: _deform(a, off, sd[key], use_torchvision)
     o0 = F.leaky_relu(_bn(dc(x, c0, "conv0.conv.weight"), sd, "conv0.normalization"), 0.2)
     rec("conv0", o0)

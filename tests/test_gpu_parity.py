@@ -98,16 +98,16 @@ def test_single_pass_fp16_error_bound(dev, stage):
 
 
 @pytest.mark.parametrize("shape", [(1, 4, 4), (2, 20, 36), (3, 72, 100), (1, 132, 68)])
-def test_first_layer_kernel_matches_tap_mode_and_oracle(dev, shape, monkeypatch):
+def test_first_layer_kernel_matches_tap_mode_and_oracle(dev, shape):
     """GeneratorJ.conv0 (models.py:44-46) in fp16 mode runs the im2col-free kernel (conv_first.cu: no-swizzle UMMA
-    operand read from the halo tile); DSU_FIRST=0 sends it through the tap-mode kernel.  Both compute the same fp16
+    operand read from the halo tile); knob first=0 sends it through the tap-mode kernel.  Both compute the same fp16
     products with fp32 accumulation, so conv0 may differ by accumulation order only (<= 1 fp16 ulp of its range)."""
     b, h, w = shape
     m, sd = _model(2, dev, precision="fp16")
     x = _frames_tensor(b, h, w, seed=11, stage=2)
     out = {}
     for mode in ("0", "1"):
-        monkeypatch.setenv("DSU_FIRST", mode)
+        m.set_knob("first", int(mode))
         with torch.no_grad():
             y = m(x.to(dev)).cpu()
         out[mode] = (y, m.debug_buffer(0, 0, (b, h, w, 40)).float()[..., :32])
@@ -140,6 +140,61 @@ def test_nondefault_offsets_builtin_table(dev, stage):
     with torch.no_grad():
         y = m(x.to(dev)).cpu()
     assert (y - _oracle(stage, sd, x)).abs().max().item() < TOL
+
+
+# ------------------------------------------------------------------ the benchmark size itself (BASELINE configs[1] / [2])
+FP16_BOUND = 1e-2     # stated bound of the single-pass fp16 mode at 512x512 (measured 3-5e-3; the reference's own default GPU
+                      # path - cuDNN TF32, the same 10-bit mantissa - sits at the same level, see bench.py gpu_baseline)
+_ORACLE_CACHE = {}
+
+
+def _oracle_cached(stage, size, seed):
+    """One CPU-oracle forward per (stage, size): ~35 s for stage 1 at 512x512 on 8 cores, so it is shared by the
+    fp16x3 and fp16 checks of the same frame."""
+    key = (stage, size, seed)
+    if key not in _ORACLE_CACHE:
+        torch.set_num_threads(min(32, len(os.sched_getaffinity(0))))
+        sd = synth.to_torch_state_dict(synth.make_state_dict(stage, seed=1234, out_gain=0.25))
+        x = _frames_tensor(1, size, size, seed=seed, stage=stage)
+        _ORACLE_CACHE[key] = (sd, x, _oracle(stage, sd, x))
+    return _ORACLE_CACHE[key]
+
+
+@pytest.mark.parametrize("stage,size", [(1, 512), (2, 512), (1, 528)])
+def test_benchmark_size_parity(dev, stage, size):
+    """One full-size frame against the CPU oracle: the RIC stencil tables of the 512 / 256 / 128 (and 528 / 264 / 132)
+    levels, partial tiles and the persistent tile schedulers are exercised where bench.py measures.  fp16x3 (the mode
+    bench.py reports as `value`) must meet the north_star's 1e-3; the fp16 mode is held to its stated bound."""
+    sd, x, ref = _oracle_cached(stage, size, seed=40 + stage)
+    errs = {}
+    for prec in ("fp16x3", "fp16"):
+        m, _ = _model(stage, dev, precision=prec)
+        with torch.no_grad():
+            y = m(x.to(dev)).cpu()
+        errs[prec] = (y - ref).abs().max().item()
+        del m
+    print("stage %d %dx%d max|dy|: fp16x3 %.3e, fp16 %.3e" % (stage, size, size, errs["fp16x3"], errs["fp16"]))
+    assert errs["fp16x3"] < TOL
+    assert errs["fp16"] < FP16_BOUND
+
+
+def test_reference_on_gpu_agrees_with_cpu_oracle(dev):
+    """bench.py's parity gate checks the engine against the oracle port run on cuda with TF32 off; that checker itself is
+    pinned to the CPU oracle here (same port code, torch's CUDA kernels instead of its CPU kernels)."""
+    for stage in (1, 2):
+        sd = synth.to_torch_state_dict(synth.make_state_dict(stage, seed=1234, out_gain=0.25))
+        x = _frames_tensor(1, 96, 80, seed=9, stage=stage)
+        ref = _oracle(stage, sd, x)
+        old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            sdd = {k: v.to(dev) for k, v in sd.items()}
+            with torch.no_grad():
+                y = (rp.generator_j_ric_forward(sdd, x.to(dev), use_torchvision=True) if stage == 1
+                     else rp.generator_j_forward(sdd, x.to(dev))).cpu()
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+        assert (y - ref).abs().max().item() < 2e-5
 
 
 # ------------------------------------------------------------------ size-independent properties at full size
@@ -339,7 +394,8 @@ def test_flop_model_and_launch_count(dev):
     assert abs(m1.algorithmic_flops(1, 512, 512) - 297.56e9) / 297.56e9 < 1e-3
     assert abs(m2.algorithmic_flops(1, 512, 512) - 543.72e9) / 543.72e9 < 1e-3
     # ingest + fused convs (+ RIC tap expansion of the input and 2 max-pools in stage 1; its dead smoother conv is not launched)
-    assert m1.kernel_launches(1, 512, 512) == 1 + 21 + 3 and m2.kernel_launches(1, 512, 512) == 1 + 22
+    # stage 1 fp16x3: conv0 = tap expansion + contraction (2 launches); stage 2: each nearest-x2 up-convolution is four sub-pixel launches
+    assert m1.kernel_launches(1, 512, 512) == 1 + 21 + 3 and m2.kernel_launches(1, 512, 512) == 1 + 22 + 6
 
 
 def test_profile_hook_reports_every_launch(dev):
@@ -352,7 +408,7 @@ def test_profile_hook_reports_every_launch(dev):
         rows = m.profile_layers(1, 64, 64, reps=1)
         assert len(rows) == m.kernel_launches(1, 64, 64) - 1
         names = [r[0] for r in rows]
-        assert names[-1] == "conv_11_a.3" and "upconv1" in names and ("ric_expand" in names) == (stage == 1)
+        assert names[-1] == "conv_11_a.3" and any(n.startswith("upconv1") for n in names) and ("ric_expand" in names) == (stage == 1)
         assert all(ms > 0 for _, ms, _ in rows)
         assert abs(sum(f for _, _, f in rows) - m.algorithmic_flops(1, 64, 64)) / m.algorithmic_flops(1, 64, 64) < 1e-6
 
@@ -375,3 +431,57 @@ def test_multi_gpu_shard_equivalence(dev):
         if r == 0:
             single = pipe.run(*(torch.from_numpy(a).to(d) for a in (color, pos, edge))).cpu()
     assert torch.equal(torch.cat(outs), single)
+
+
+# ------------------------------------------------------------------ the UNMODIFIED reference scripts on the engine
+def _reference_dir():
+    for cand in (os.environ.get("DSU_REFERENCE_DIR"), "/root/reference/3_style_translator",
+                 os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "_refcopy", "3_style_translator")):
+        if cand and os.path.exists(os.path.join(cand, "test_stage1.py")):
+            return cand
+    return None
+
+
+def test_unmodified_reference_scripts_run_on_the_engine(dev, tmp_path):
+    """`python -m drawingspinup_b200.run <reference>/test_stage1.py --uid u`, then test_stage2.py, on a
+    synthetic <uid> tree; the PNGs the reference's own loop writes are compared with the oracle chain (<= 1 LSB).
+    The scripts, training/*.py and configs/*.yaml are used IN PLACE through symlinks (nothing of the reference is
+    copied or edited); only the relative dataset root `../dataset/AnimatedDrawings/preprocessed` (config_stage1.yaml:76)
+    resolves into the temporary tree.  Skipped where the reference checkout is absent (the GPU box of the driver)."""
+    import subprocess
+    import sys
+    from PIL import Image
+    ref = _reference_dir()
+    if ref is None:
+        pytest.skip("reference checkout not present (set DSU_REFERENCE_DIR)")
+    work = tmp_path / "3_style_translator"
+    work.mkdir()
+    for name in ("test_stage1.py", "test_stage2.py", "training", "configs"):
+        os.symlink(os.path.join(ref, name), work / name)
+    root = tmp_path / "dataset" / "AnimatedDrawings" / "preprocessed"
+    uid, h, w, n = "synthetic0001", 64, 48, 3
+    sd1 = synth.to_torch_state_dict(synth.make_state_dict(1, out_gain=0.25))
+    sd2 = synth.to_torch_state_dict(synth.make_state_dict(2, out_gain=0.25))
+    stacks = synth.write_character_tree(str(root), uid, {"dab": n}, h, w, seed=5, state_dicts=(sd1, sd2))
+    color, pos, edge = stacks["dab"]
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=repo + os.pathsep + os.environ.get("PYTHONPATH", ""), DSU_PRECISION="fp16x3")
+    for script in ("test_stage1.py", "test_stage2.py"):
+        r = subprocess.run([sys.executable, "-m", "drawingspinup_b200.run", str(work / script), "--uid", uid],
+                           env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+        assert "Testing finished" in r.stdout
+    base = root / uid / "mesh" / "blender_render" / "dab"
+    got1 = np.stack([np.array(Image.open(base / "res_stage1_mask_pos" / ("%04d.png" % i))) for i in range(n)])
+    got2 = np.stack([np.array(Image.open(base / "res_stage2_mask_pos_edge" / ("%04d.png" % i))) for i in range(n)])
+    with torch.no_grad():
+        x1 = torch.from_numpy(np.stack([rp.frame_to_tensor(color[i], pos[i])[0] for i in range(n)]))
+        y1 = rp.generator_j_ric_forward(sd1, x1, use_torchvision=True)
+        want1 = np.stack([rp.compose_rgba(y1[i].numpy(), rp.frame_to_tensor(color[i], pos[i])[1]) for i in range(n)])
+        # stage 2 reads stage 1's PNGs back from disk (config_stage2.yaml:61 pre_dir) - use the bytes the engine wrote
+        x2 = torch.from_numpy(np.stack([rp.frame_to_tensor(got1[i], pos[i], edge[i])[0] for i in range(n)]))
+        y2 = rp.generator_j_forward(sd2, x2)
+        want2 = np.stack([rp.compose_rgba(y2[i].numpy(), rp.frame_to_tensor(got1[i], pos[i])[1]) for i in range(n)])
+    for got, want in ((got1, want1), (got2, want2)):
+        d = np.abs(got.astype(np.int32) - want.astype(np.int32))
+        assert got.shape == want.shape and d.max() <= 1 and (d > 0).mean() < 0.01

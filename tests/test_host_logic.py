@@ -102,6 +102,42 @@ def test_install_rebinds_reference_names():
     assert isinstance(model, dsu.GeneratorJ_RIC)
 
 
+def test_real_build_model_returns_engine_classes():
+    """The real factory seam (trainers.py:33-35) with the real reference modules: after install() the UNMODIFIED
+    ``training.trainers.build_model`` constructs the engine classes, and a state dict produced by the reference's own
+    classes loads strictly (same 89 keys, same order); uninstall() restores the reference classes.  Needs the reference
+    checkout (present in the build container; skipped elsewhere)."""
+    ref = os.environ.get("DSU_REFERENCE_DIR", "/root/reference/3_style_translator")
+    if not os.path.exists(os.path.join(ref, "training", "trainers.py")):
+        pytest.skip("reference checkout not present")
+    saved = {k: v for k, v in sys.modules.items() if k == "training" or k.startswith("training.")}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, ref)
+    try:
+        import importlib
+        m = importlib.import_module("training.models")
+        t = importlib.import_module("training.trainers")
+        args = dict(DEFAULT_ARGS)
+        ref_models = {name: t.build_model(name, dict(args), "cpu") for name in ("GeneratorJ", "GeneratorJ_RIC")}
+        assert all(type(v).__module__ == "training.models" for v in ref_models.values())
+        dsu.install(m)
+        for name, cls in (("GeneratorJ", dsu.GeneratorJ), ("GeneratorJ_RIC", dsu.GeneratorJ_RIC)):
+            eng = t.build_model(name, dict(args), "cpu")            # the unmodified factory, call-time getattr
+            assert type(eng) is cls
+            sd = ref_models[name].state_dict()
+            eng.load_state_dict(sd)                                   # strict
+            assert list(eng.state_dict().keys()) == list(sd.keys())
+            assert all(torch.equal(a, b) for a, b in zip(eng.state_dict().values(), sd.values()))
+        dsu.uninstall(m)
+        assert type(t.build_model("GeneratorJ", dict(args), "cpu")).__module__ == "training.models"
+    finally:
+        sys.path.remove(ref)
+        for k in [k for k in sys.modules if k == "training" or k.startswith("training.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
 def test_launcher_runs_script_with_rebound_classes(tmp_path, monkeypatch, capsys):
     """drawingspinup_b200.run on a miniature stand-in for 3_style_translator: the script resolves the
     class through training.models exactly like trainers.build_model does."""
@@ -217,7 +253,7 @@ def test_algorithmic_flop_model_matches_baseline_md():
 
 
 def test_subpixel_decomposition_of_upsample_conv_is_exact():
-    """The experimental DSU_SUBPIXEL plan (engine.cu compile_layer / conv_halo_persist_kernel<true>) replaces
+    """The sub-pixel plan of stage 2 (default; engine.cu compile_layer / conv_halo_persist_kernel<true>) replaces
     nearest-x2 + 3x3 conv (models.py:180-192) by four 2x2 convolutions on the low-resolution tensor.  Same index
     arithmetic restated with torch: class (py, px) writes out[2y+py, 2x+px], tap (a, b) reads in[y+a-1+py, x+b-1+px]
     with the 3x3 weights that hit that source pixel summed - equal to the reference composition including the border."""
