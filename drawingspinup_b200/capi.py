@@ -41,6 +41,7 @@ SYMBOLS = {
     "dsu_loaded_keys": (C.c_int, [_VP]),
     "dsu_finalize": (C.c_int, [_VP, _VP]),
     "dsu_set_knob": (C.c_int, [_VP, C.c_char_p, _I32]),
+    "dsu_debug_watchdog": (C.c_int, [_VP, C.POINTER(C.c_uint64), _I32]),
     "dsu_set_ric_offsets": (C.c_int, [_VP, _I32, _I32, _VP]),
     "dsu_forward": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _VP, _VP]),
     "dsu_forward_u8": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _I32, _VP, _VP, _VP]),

@@ -1,5 +1,6 @@
 // Parameter blocks shared by the fused convolution kernel and the engine that plans a network.
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -67,6 +68,10 @@ struct EpiParams {
     __half* out2_hi;        // second, un-ReLU'd copy (skip connection) or null
     __half* out2_lo;
     int out2_pitch, out2_choff;
+    // stage 1 in split-fp16 mode keeps its activations in fp32 (same bytes as hi + lo planes; the RIC producers blend in fp32
+    // anyway and split after the blend): when non-null these replace out_hi/out_lo and out2_hi/out2_lo (same pitch / choff)
+    float* out_f32;
+    float* out2_f32;
     // fused conv_12 (1x1, +bias, optional tanh) tail
     const float* w12;       // [3][Cout] or null
     const float* b12;       // [3]
@@ -107,6 +112,38 @@ struct ConvParams {
     int sub, sub_py, sub_px, pad_y, pad_x;
     int raw_choff;          // conv_ric_first.cu (experimental): first channel of the raw network input inside seg[0]
 };
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// RIC convolution with the A operand in TENSOR MEMORY (conv_ric_tm.cu): the stage-1 kernel of round 2.
+// A "block" is what one TMA tensor load stages: 128 bytes of source channels per halo pixel (64 fp16 channels, or 32 fp32
+// channels in split-fp16 mode) from one contiguous channel run of one buffer; it feeds up to two "stages" of 4 16-byte
+// chunks each.  A stage is one hand-off unit: 144 TMEM columns of blended taps + its weight tiles + one commit.
+constexpr int kTmMaxBlocks = 12;
+constexpr int kTmMaxMaps = 3;
+constexpr int kTmStageCols = 144;        // 9 taps x 2 parts x 8 columns (fp16: two K16 steps; split-fp16: hi and lo of one K16 step)
+constexpr int kTmHaloBytes = 23552;      // 18 x 10 pixel lines of 128 B, rounded up to the 1024-byte swizzle atom
+constexpr int kTmProducerWarps = 8, kTmEpilogueWarps = 4, kTmIssuerWarps = 6, kTmLoaderWarps = 2;
+constexpr int kTmThreads = (kTmProducerWarps + kTmEpilogueWarps + kTmIssuerWarps + kTmLoaderWarps) * 32;
+struct TmBlock {
+    uint8_t map;            // tensor map (channel run) index
+    uint8_t nstages;        // stages of this block that carry weights (1 or 2)
+    uint8_t chunks[2];      // 16-byte chunks with real channels per stage (1..4); the rest reads zeros
+    uint16_t c0;            // first channel of the block inside its run (elements)
+    uint16_t pad_;
+};
+struct TmParams {
+    ConvParams c;           // output geometry, stencil tables and the epilogue (shared with the other kernels)
+    alignas(64) CUtensorMap tmap[kTmMaxMaps];
+    TmBlock blk[kTmMaxBlocks];
+    int nblocks, nstages;   // per tile
+    int sa, sb, nsets, ni;  // TMEM A stages, weight stages in shared memory (multiple of sa), accumulator sets, issuing warps
+    int halo_w, halo_h;     // 18 x 10 (or 10 x 6 with the fused nearest x2)
+    int b_stage_bytes;      // Cout * 576: 9 taps x 2 parts x (Cout x 32 B no-swizzle tile)
+    const uint8_t* wpack;   // [stage][tap][part][Cout x 32 B]
+    unsigned long long* dbg;    // watchdog records (pinned host memory, one slot per warp) or null
+};
+cudaError_t launch_conv_ric_tm(const TmParams& p, cudaStream_t stream);
+size_t conv_ric_tm_smem_bytes(int cout, int sb);
 
 cudaError_t launch_conv(const ConvParams& p, cudaStream_t stream);
 cudaError_t launch_conv_halo(const ConvParams& p, cudaStream_t stream);

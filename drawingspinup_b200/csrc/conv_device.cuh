@@ -85,6 +85,19 @@ __device__ __forceinline__ void store32(__half* hi, __half* lo, const float* f) 
     }
 }
 
+// 32 channels of one pixel -> fp32 NHWC (stage-1 activations of the split-fp16 mode); 32-byte aligned rows take 256-bit stores
+__device__ __forceinline__ void store32_f32(float* dst, const float* f) {
+    if ((reinterpret_cast<uintptr_t>(dst) & 31u) == 0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            st_global_256(dst + 8 * c, make_uint4(__float_as_uint(f[8 * c]), __float_as_uint(f[8 * c + 1]), __float_as_uint(f[8 * c + 2]), __float_as_uint(f[8 * c + 3])),
+                          make_uint4(__float_as_uint(f[8 * c + 4]), __float_as_uint(f[8 * c + 5]), __float_as_uint(f[8 * c + 6]), __float_as_uint(f[8 * c + 7])));
+    } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) reinterpret_cast<float4*>(dst)[c] = make_float4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]);
+    }
+}
+
 // One 32-column batch of one accumulator row after the K-split partial sums were added: folded BN / bias, activation,
 // optional post-activation affine, residual stream, fp16 stores, conv_12 partial dot products.  The activation, the
 // second affine and the lo plane are compile-time (dispatched once per row in epilogue_row): with run-time tests inside
@@ -141,14 +154,16 @@ __device__ __forceinline__ void epilogue_batch(const ConvParams& p, const float*
 #pragma unroll
         for (int c = 0; c < 8; ++c) rp[c] = make_float4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]);
     }
-    if (e.out2_hi)
+    if (e.out2_f32) store32_f32(e.out2_f32 + opix * e.out2_pitch + e.out2_choff + cb, f);
+    else if (e.out2_hi)
         store32<kLo>(e.out2_hi + opix * e.out2_pitch + e.out2_choff + cb,
                      e.out2_lo ? e.out2_lo + opix * e.out2_pitch + e.out2_choff + cb : nullptr, f);
     if (e.out_relu) {
 #pragma unroll
         for (int c = 0; c < 32; ++c) f[c] = fmaxf(f[c], 0.0f);
     }
-    if (e.out_hi)
+    if (e.out_f32) store32_f32(e.out_f32 + opix * e.out_pitch + e.out_choff + cb, f);
+    else if (e.out_hi)
         store32<kLo>(e.out_hi + opix * e.out_pitch + e.out_choff + cb,
                      e.out_lo ? e.out_lo + opix * e.out_pitch + e.out_choff + cb : nullptr, f);
     if (tail) {

@@ -64,6 +64,14 @@ struct LayerDef {
     // wk = 3 is the kernel size of the stored weights; -1 = ordinary layer
     int sub = -1, wk = 0;
     int raw_buf = -1, raw_choff = 0;   // expanded stage-1 conv0: where the un-expanded 8-channel input lives (conv_ric_first.cu)
+    // tensor-memory RIC kernel (conv_ric_tm.cu): channel runs (one TMA tensor map each), 128-byte blocks, packed weights
+    int tm = 0;
+    struct TmRun { int buf, choff, nch, wch0, wn; };
+    std::vector<TmRun> tm_runs;
+    std::vector<TmBlock> tm_blocks;
+    int tm_nstages = 0;
+    uint8_t* d_wpack_tm = nullptr;
+    CUtensorMap tm_maps[kTmMaxMaps];
     // compiled at finalize
     int nchunks = 0, nblocks = 0;
     uint32_t kmask_full = 0xF, kmask_last = 0xF, kmask2_full = 0, kmask2_last = 0;
@@ -90,6 +98,8 @@ struct Knobs {
     int first_ks = 0, first_na = 0, first_sets = 0;
     int halo_persist = 2, halo_ns = 0, halo_ks = 0, halo_na = 0, halo_sb = 0, halo_tps = 0;
     int subpixel = 1;         // plan-time: stage-2 nearest-x2 + 3x3 as four 2x2 sub-pixel convolutions
+    int ric_tm = 1;           // plan-time: stage 1 runs the tensor-memory RIC kernel (conv_ric_tm.cu); 0 = the round-1 kernels
+    int tm_ni = 0, tm_sb = 0; // tensor-memory kernel: issuing warps / weight stages (0 = planner decides)
 };
 struct KnobName { const char* name; int Knobs::*field; };
 const KnobName kKnobNames[] = {
@@ -97,7 +107,7 @@ const KnobName kKnobNames[] = {
     {"ric_ks", &Knobs::ric_ks}, {"first", &Knobs::first}, {"first_ks", &Knobs::first_ks}, {"first_na", &Knobs::first_na},
     {"first_sets", &Knobs::first_sets}, {"halo_persist", &Knobs::halo_persist}, {"halo_ns", &Knobs::halo_ns},
     {"halo_ks", &Knobs::halo_ks}, {"halo_na", &Knobs::halo_na}, {"halo_sb", &Knobs::halo_sb}, {"halo_tps", &Knobs::halo_tps},
-    {"subpixel", &Knobs::subpixel},
+    {"subpixel", &Knobs::subpixel}, {"ric_tm", &Knobs::ric_tm}, {"tm_ni", &Knobs::tm_ni}, {"tm_sb", &Knobs::tm_sb},
 };
 Knobs knobs_from_env() {
     Knobs k;
@@ -145,6 +155,11 @@ struct dsu_engine {
     std::set<std::string> loaded;
     std::vector<LayerDef> layers;
     std::vector<Step> steps;
+    unsigned long long* wd_host = nullptr;   // watchdog records of the tensor-memory kernel (pinned, device-mapped)
+    unsigned long long* wd_dev = nullptr;
+    bool ric_tm = false;      // stage 1 on the tensor-memory kernel
+    bool f32_acts = false;    // ... and (split-fp16 mode) its activation buffers hold fp32 instead of fp16 hi + lo planes
+    int maps_B = 0, maps_H = 0, maps_W = 0;
     int buf_level[NBUF]{}, buf_C[NBUF]{};
     bool buf_used[NBUF]{};
     float *d_w12 = nullptr, *d_b12 = nullptr;
@@ -221,7 +236,7 @@ int build_plan(dsu_engine* E) {
     setbuf(SK0, 0, f[0] + cp);
     setbuf(O1, 1, f[1]);
     setbuf(O2, 2, f[2]);
-    if (ric) { setbuf(P0, 1, f[0]); setbuf(P1, 2, f[1]); setbuf(EXP0, 0, 9 * cp); }
+    if (ric) { setbuf(P0, 1, f[0]); setbuf(P1, 2, f[1]); if (!E->ric_tm) setbuf(EXP0, 0, 9 * cp); }
     if (c.resnet_blocks > 0) { setbuf(TT, 2, f[2]); setbuf(UU, 2, f[2]); }
     setbuf(V2, 1, f[4]);
     setbuf(V1, 0, f[4]);
@@ -235,7 +250,7 @@ int build_plan(dsu_engine* E) {
         LayerDef L; L.name = "conv0"; L.wkey = "conv0.conv.weight"; L.bkey = bias_of("conv0.conv");
         L.bn = bn ? "conv0.normalization" : ""; L.k = k0; L.pad = k0 / 2; L.ric = ric; L.cout = f[0]; L.level_out = 0;
         L.segs = {{SK0, f[0], cp, 0, cin}}; L.act = 2; L.out_buf = SK0; L.out_choff = 0;
-        if (ric) {   // sample the 9 taps of the 8-channel input once, then contract over 9 * cp channels
+        if (ric && !E->ric_tm) {   // round-1 path: sample the 9 taps of the 8-channel input once, then contract over 9 * cp channels
             E->steps.push_back(Step{2, -1, SK0, f[0], cp, EXP0});
             L.ric = 0; L.expanded = 1; L.segs = {{EXP0, 0, cp, 0, cin}};
             L.raw_buf = SK0; L.raw_choff = f[0];
@@ -316,6 +331,8 @@ int build_plan(dsu_engine* E) {
         L.segs = {{ric ? C11 : S0, 0, f[5], 0, f[5]}}; L.act = 1; L.final = 1;
         add(L);
     }
+    if (E->ric_tm)
+        for (LayerDef& L : E->layers) L.tm = L.ric ? 1 : 0;
     return DSU_OK;
 }
 
@@ -327,6 +344,70 @@ int upload(T** dst, const std::vector<T>& src) {
     CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(dst), src.size() * sizeof(T)));
     CUDA_TRY(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
     return DSU_OK;
+}
+
+// Tensor-memory RIC kernel (conv_ric_tm.cu): channel runs -> 128-byte blocks -> stages, and the weights as
+// [stage][tap][part][Cout x 32 B] no-swizzle K-major tiles (8-row x 16-byte core matrices: element (o, c) of a 16-channel
+// K step at (o / 8) * 256 + (c / 8) * 128 + (o % 8) * 16 + (c % 8) * 2; descriptor LBO = 128, SBO = 256 - tools/umma_ts_probe.cu).
+// fp16 mode: a stage = 32 channels = two K16 steps (part = step).  split-fp16: a stage = 16 fp32 channels = one K16 step,
+// part 0 = W_hi, part 1 = W_lo = fp16(W - W_hi).
+int compile_tm(dsu_engine* E, LayerDef& L, const std::vector<float>& Wt, int cin_total) {
+    const bool exact = E->exact;
+    const int C = L.cout, k = L.k;
+    if (k != 3 || L.stride != 1) return fail(DSU_E_INVALID, "tensor-memory RIC kernel: 3x3 stride-1 layers only: " + L.name);
+    // consecutive segments that continue each other in the same buffer AND in the weight's input channels form one run
+    L.tm_runs.clear();
+    for (const SegDef& sg : L.segs) {
+        if (!L.tm_runs.empty()) {
+            LayerDef::TmRun& r = L.tm_runs.back();
+            if (r.buf == sg.buf && r.choff + r.nch == sg.choff && r.wch0 + r.nch == sg.wch0 && r.wn == r.nch) {
+                r.nch += sg.nch; r.wn += sg.wn;
+                continue;
+            }
+        }
+        L.tm_runs.push_back(LayerDef::TmRun{sg.buf, sg.choff, sg.nch, sg.wch0, sg.wn});
+    }
+    if (L.tm_runs.size() > kTmMaxMaps) return fail(DSU_E_INVALID, "tensor-memory RIC kernel: too many concat runs: " + L.name);
+    const int bs = exact ? 32 : 64, ss = bs / 2, chunk_ch = exact ? 4 : 8;     // channels per block / stage / 16-byte chunk
+    L.tm_blocks.clear();
+    struct StageSrc { int run, c0; };          // first run channel of the stage
+    std::vector<StageSrc> stages;
+    for (size_t ri = 0; ri < L.tm_runs.size(); ++ri) {
+        const LayerDef::TmRun& r = L.tm_runs[ri];
+        for (int c0 = 0; c0 < r.nch; c0 += bs) {
+            const int nch = std::min(bs, r.nch - c0);
+            TmBlock b{};
+            b.map = static_cast<uint8_t>(ri);
+            b.c0 = static_cast<uint16_t>(c0);
+            b.nstages = static_cast<uint8_t>(nch > ss ? 2 : 1);
+            for (int h = 0; h < b.nstages; ++h) {
+                b.chunks[h] = static_cast<uint8_t>((std::min(ss, nch - h * ss) + chunk_ch - 1) / chunk_ch);
+                stages.push_back(StageSrc{static_cast<int>(ri), c0 + h * ss});
+            }
+            L.tm_blocks.push_back(b);
+        }
+    }
+    if (L.tm_blocks.size() > kTmMaxBlocks) return fail(DSU_E_INVALID, "tensor-memory RIC kernel: too many channel blocks: " + L.name);
+    L.tm_nstages = static_cast<int>(stages.size());
+    const size_t tile = static_cast<size_t>(C) * 32, stage_bytes = tile * 18;
+    std::vector<uint8_t> pack(stages.size() * stage_bytes, 0);
+    for (size_t si = 0; si < stages.size(); ++si) {
+        const LayerDef::TmRun& r = L.tm_runs[stages[si].run];
+        for (int t = 0; t < 9; ++t)
+            for (int part = 0; part < 2; ++part) {
+                uint8_t* dst = pack.data() + si * stage_bytes + (static_cast<size_t>(t) * 2 + part) * tile;
+                for (int o = 0; o < C; ++o)
+                    for (int c = 0; c < 16; ++c) {
+                        const int rc = stages[si].c0 + (exact ? c : 16 * part + c);      // channel inside the run
+                        if (rc >= r.wn) continue;                                          // K padding: zero weight
+                        const float wv = Wt[((static_cast<size_t>(o) * cin_total + r.wch0 + rc) * 3 + t / 3) * 3 + t % 3];
+                        const __half wh = __float2half_rn(wv);
+                        const __half val = (exact && part == 1) ? __float2half_rn(wv - __half2float(wh)) : wh;
+                        std::memcpy(dst + (o / 8) * 256 + (c / 8) * 128 + (o % 8) * 16 + (c % 8) * 2, &val, 2);
+                    }
+            }
+    }
+    return upload(&L.d_wpack_tm, pack);
 }
 
 int compile_layer(dsu_engine* E, LayerDef& L) {
@@ -363,6 +444,13 @@ int compile_layer(dsu_engine* E, LayerDef& L) {
     const std::vector<float>& Wt = L.sub >= 0 ? Wsub : E->w.at(L.wkey);
     if (Wt.size() != static_cast<size_t>(C) * cin_total * k * k) return fail(DSU_E_INVALID, "weight size mismatch for " + L.wkey);
 
+    double real_k_tm = 0;
+    for (const SegDef& sg : L.segs) real_k_tm += static_cast<double>(sg.wn) * k * k;
+    if (L.tm) {
+        L.macs_per_px = real_k_tm * C;
+        int rc_tm = compile_tm(E, L, Wt, cin_total);
+        if (rc_tm) return rc_tm;
+    } else {
     // A "data slot" is 8 input channels of one concat segment at one tap.  A chunk (8 smem slots =
     // 64 K elements) holds 8 data slots (fp16 mode) or 4 data slots as [hi x4 | lo x4] (exact mode).
     // plain conv: data slots are packed densely over (tap, segment, channel group);
@@ -487,9 +575,11 @@ int compile_layer(dsu_engine* E, LayerDef& L) {
     pack.resize(off);
     L.kmask_full = hdrs.front().kmask; L.kmask2_full = hdrs.front().kmask2;
     L.kmask_last = hdrs.back().kmask; L.kmask2_last = hdrs.back().kmask2;
+    int rc_up;
+    if ((rc_up = upload(&L.d_slots, slots))) return rc_up;
+    if ((rc_up = upload(&L.d_wpack, pack))) return rc_up;
+    }
     int rc;
-    if ((rc = upload(&L.d_slots, slots))) return rc;
-    if ((rc = upload(&L.d_wpack, pack))) return rc;
 
     // epilogue affine: y = act(acc * scale + shift) [* scale2 + shift2]
     std::vector<float> scale(C, 1.0f), shift(C, 0.0f), scale2, shift2;
@@ -607,6 +697,45 @@ int build_level(dsu_engine* E, Level& lv, int h, int w) {
     return DSU_OK;
 }
 
+// ------------------------------------------------------------------ TMA tensor maps of the tensor-memory RIC layers
+// One 4-D map (channel, x, y, frame) per channel run of a layer's input concat: base = first channel of the run, extent =
+// the run's channels, so that everything outside the run / the image reads as zero.  Box = 128 bytes of channels x the halo
+// tile of an 8 x 16 output tile (18 x 10 pixels; 10 x 6 source pixels when the layer's nearest x2 is folded in), SWIZZLE_128B.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int build_tensor_maps(dsu_engine* E, int B, int H, int W) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) return fail(DSU_E_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    const size_t esz = E->f32_acts ? sizeof(float) : sizeof(__half);
+    for (LayerDef& L : E->layers) {
+        if (!L.tm) continue;
+        for (size_t ri = 0; ri < L.tm_runs.size(); ++ri) {
+            const LayerDef::TmRun& r = L.tm_runs[ri];
+            const int lvl = E->buf_level[r.buf];
+            const cuuint64_t hs = static_cast<cuuint64_t>(H >> lvl), ws = static_cast<cuuint64_t>(W >> lvl);
+            const cuuint64_t pitch_b = static_cast<cuuint64_t>(E->buf_C[r.buf]) * esz;
+            const cuuint64_t dims[4] = {static_cast<cuuint64_t>(r.nch), ws, hs, static_cast<cuuint64_t>(B)};
+            const cuuint64_t strides[3] = {pitch_b, pitch_b * ws, pitch_b * ws * hs};
+            const cuuint32_t box[4] = {static_cast<cuuint32_t>(128 / esz), L.up ? 10u : 18u, L.up ? 6u : 10u, 1u};
+            const cuuint32_t estr[4] = {1, 1, 1, 1};
+            void* basep = reinterpret_cast<uint8_t*>(E->buf_hi[r.buf]) + static_cast<size_t>(r.choff) * esz;
+            const CUresult cr = encode(&L.tm_maps[ri], E->f32_acts ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, basep,
+                                       dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (cr != CUDA_SUCCESS)
+                return fail(DSU_E_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string(static_cast<int>(cr)) + ") for " + L.name);
+        }
+    }
+    return DSU_OK;
+}
+
 // ------------------------------------------------------------------ workspace
 int ensure_shape(dsu_engine* E, int B, int H, int W) {
     if (B <= 0 || H <= 0 || W <= 0 || (H % 4) || (W % 4))
@@ -614,14 +743,16 @@ int ensure_shape(dsu_engine* E, int B, int H, int W) {
     for (int b = 0; b < NBUF; ++b) {
         if (!E->buf_used[b]) continue;
         const int l = E->buf_level[b];
-        const size_t bytes = static_cast<size_t>(B) * (H >> l) * (W >> l) * E->buf_C[b] * sizeof(__half);
+        // f32_acts: one fp32 plane (same bytes as the fp16 hi + lo planes) behind buf_hi, no lo plane
+        const size_t bytes = static_cast<size_t>(B) * (H >> l) * (W >> l) * E->buf_C[b] * (E->f32_acts ? sizeof(float) : sizeof(__half));
         if (bytes > E->buf_cap[b]) {
             if (E->buf_hi[b]) cudaFree(E->buf_hi[b]);
             if (E->buf_lo[b]) cudaFree(E->buf_lo[b]);
             E->buf_hi[b] = E->buf_lo[b] = nullptr;
+            E->maps_B = 0;                                   // tensor maps point into the old allocation
             CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&E->buf_hi[b]), bytes));
             CUDA_TRY(cudaMemset(E->buf_hi[b], 0, bytes));
-            if (E->exact) {
+            if (E->exact && !E->f32_acts) {
                 CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&E->buf_lo[b]), bytes));
                 CUDA_TRY(cudaMemset(E->buf_lo[b], 0, bytes));
             }
@@ -640,6 +771,11 @@ int ensure_shape(dsu_engine* E, int B, int H, int W) {
             if (rc) return rc;
         }
     E->B = B; E->H = H; E->W = W;
+    if (E->ric_tm && (E->maps_B != B || E->maps_H != H || E->maps_W != W)) {
+        int rc = build_tensor_maps(E, B, H, W);
+        if (rc) return rc;
+        E->maps_B = B; E->maps_H = H; E->maps_W = W;
+    }
     return DSU_OK;
 }
 
@@ -675,6 +811,11 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
         ++step_idx;
         if (sp.type == 1) {
             const int l = E->buf_level[sp.src];
+            if (E->f32_acts) {
+                CUDA_TRY(maxpool2_f32(reinterpret_cast<const float*>(E->buf_hi[sp.src]), E->buf_C[sp.src], sp.src_choff, B, H >> l, W >> l,
+                                      sp.C, reinterpret_cast<float*>(E->buf_hi[sp.dst]), E->buf_C[sp.dst], st));
+                continue;
+            }
             CUDA_TRY(maxpool2(E->buf_hi[sp.src], E->buf_lo[sp.src], E->buf_C[sp.src], sp.src_choff, B, H >> l, W >> l, sp.C,
                               E->buf_hi[sp.dst], E->buf_lo[sp.dst], E->buf_C[sp.dst], st));
             continue;
@@ -723,14 +864,49 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
         if (L.out_buf >= 0) {
             e.out_hi = E->buf_hi[L.out_buf]; e.out_lo = E->buf_lo[L.out_buf];
             e.out_pitch = E->buf_C[L.out_buf]; e.out_choff = L.out_choff; e.out_relu = L.out_relu;
+            if (E->f32_acts) { e.out_f32 = reinterpret_cast<float*>(E->buf_hi[L.out_buf]); e.out_hi = nullptr; e.out_lo = nullptr; }
         }
         if (L.out2_buf >= 0) {
             e.out2_hi = E->buf_hi[L.out2_buf]; e.out2_lo = E->buf_lo[L.out2_buf];
             e.out2_pitch = E->buf_C[L.out2_buf]; e.out2_choff = 0;
+            if (E->f32_acts) { e.out2_f32 = reinterpret_cast<float*>(E->buf_hi[L.out2_buf]); e.out2_hi = nullptr; e.out2_lo = nullptr; }
         }
         if (L.final) {
             e.w12 = E->d_w12; e.b12 = E->d_b12; e.tanh_flag = E->cfg.tanh;
             e.y_nchw = y_dev; e.y_rgba = y_rgba; e.alpha_src = alpha_src; e.alpha_stride = alpha_stride;
+        }
+        if (L.tm) {
+            // tensor-memory RIC kernel: accumulator sets / A stages share the 512 TMEM columns, weight stages fill shared memory
+            TmParams T{};
+            T.c = p;
+            for (size_t i = 0; i < L.tm_runs.size(); ++i) T.tmap[i] = L.tm_maps[i];
+            T.nblocks = static_cast<int>(L.tm_blocks.size());
+            for (int i = 0; i < T.nblocks; ++i) T.blk[i] = L.tm_blocks[i];
+            T.nstages = L.tm_nstages;
+            T.sa = 2;
+            T.nsets = (2 * L.cout + T.sa * kTmStageCols <= 512) ? 2 : 1;
+            T.b_stage_bytes = L.cout * 576;
+            int sb = static_cast<int>((227 * 1024 - 2 * kTmHaloBytes - 8 * 1024) / T.b_stage_bytes);
+            sb = std::min(sb, 6);
+            if (K.tm_sb > 0) sb = std::min(sb, K.tm_sb);
+            sb = (sb / T.sa) * T.sa;
+            if (sb < T.sa) return fail(DSU_E_INVALID, "tensor-memory RIC kernel: the weight stages do not fit in shared memory: " + L.name);
+            T.sb = sb;
+            T.ni = K.tm_ni > 0 ? std::min(K.tm_ni, kTmIssuerWarps) : kTmIssuerWarps;
+            T.halo_w = L.up ? 10 : 18; T.halo_h = L.up ? 6 : 10;
+            T.wpack = L.d_wpack_tm;
+            if (!E->wd_host) {
+                if (cudaHostAlloc(reinterpret_cast<void**>(&E->wd_host), 32 * sizeof(unsigned long long), cudaHostAllocMapped) == cudaSuccess) {
+                    std::memset(E->wd_host, 0, 32 * sizeof(unsigned long long));
+                    if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&E->wd_dev), E->wd_host, 0) != cudaSuccess) E->wd_dev = nullptr;
+                } else {
+                    E->wd_host = nullptr;
+                    (void)cudaGetLastError();
+                }
+            }
+            T.dbg = E->wd_dev;
+            CUDA_TRY(launch_conv_ric_tm(T, st));
+            continue;
         }
         if (L.expanded && use_ric_first) {
             p.seg[0].ptr = E->buf_hi[L.raw_buf];
@@ -883,8 +1059,14 @@ int dsu_create(const dsu_config* cfg, dsu_handle* out) {
     dsu_engine* E = new dsu_engine();
     E->cfg = *cfg;
     E->knobs = knobs_from_env();
+    // stage 1 runs the tensor-memory RIC kernel unless a layer is wider than its TMEM budget allows (then, or with
+    // DSU_RIC_TM=0, the round-1 kernels)
+    E->ric_tm = cfg->kind == DSU_KIND_GENERATORJ_RIC && E->knobs.ric_tm != 0;
+    for (int i = 0; i < 6; ++i)
+        if (cfg->filters[i] > 224) E->ric_tm = false;
     E->cin_pad = (cfg->input_channels + 7) / 8 * 8;
     E->exact = cfg->precision == DSU_PREC_FP16X3;
+    E->f32_acts = E->ric_tm && E->exact;
     int rc = build_plan(E);
     if (rc) { delete E; return rc; }
     *out = E;
@@ -895,12 +1077,13 @@ void dsu_destroy(dsu_handle h) {
     if (!h) return;
     DeviceGuard guard(h->cfg.device);
     for (LayerDef& L : h->layers) {
-        cudaFree(L.d_slots); cudaFree(L.d_wpack);
+        cudaFree(L.d_slots); cudaFree(L.d_wpack); cudaFree(L.d_wpack_tm);
         cudaFree(L.d_scale); cudaFree(L.d_shift); cudaFree(L.d_scale2); cudaFree(L.d_shift2);
     }
     for (int b = 0; b < NBUF; ++b) { cudaFree(h->buf_hi[b]); cudaFree(h->buf_lo[b]); }
     for (int l = 0; l < 3; ++l) { cudaFree(h->lv[l].lyx); cudaFree(h->lv[l].oct); cudaFree(h->lv[l].wh); }
     cudaFree(h->resid); cudaFree(h->d_w12); cudaFree(h->d_b12);
+    if (h->wd_host) cudaFreeHost(h->wd_host);
     cudaFree(h->io_color); cudaFree(h->io_pos); cudaFree(h->io_edge); cudaFree(h->io_out);
     delete h;
 }
@@ -955,8 +1138,9 @@ int dsu_set_knob(dsu_handle h, const char* name, int32_t value) {
     if (!h || !name) return fail(DSU_E_INVALID, "null argument");
     for (const KnobName& kn : kKnobNames)
         if (std::strcmp(kn.name, name) == 0) {
-            if (kn.field == &Knobs::subpixel && h->knobs.subpixel != value)
-                return fail(DSU_E_STATE, "'subpixel' shapes the launch plan: set DSU_SUBPIXEL in the environment before dsu_create");
+            if ((kn.field == &Knobs::subpixel || kn.field == &Knobs::ric_tm) && h->knobs.*(kn.field) != value)
+                return fail(DSU_E_STATE, std::string("'") + name + "' shapes the launch plan: set DSU_" + (kn.field == &Knobs::subpixel ? "SUBPIXEL" : "RIC_TM") +
+                                             " in the environment before dsu_create");
             h->knobs.*(kn.field) = value;
             return DSU_OK;
         }
@@ -979,7 +1163,7 @@ int dsu_forward(dsu_handle h, const float* x_dev, int32_t B, int32_t H, int32_t 
     if ((rc = ensure_shape(h, B, H, W))) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CUDA_TRY(ingest_f32(x_dev, B, h->cfg.input_channels, h->cin_pad, H, W, h->buf_hi[SK0], h->buf_lo[SK0],
-                        h->buf_C[SK0], h->cfg.filters[0], st));
+                        h->f32_acts ? reinterpret_cast<float*>(h->buf_hi[SK0]) : nullptr, h->buf_C[SK0], h->cfg.filters[0], st));
     return run_network(h, B, H, W, y_dev, nullptr, nullptr, 0, st);
 }
 
@@ -993,8 +1177,8 @@ int dsu_forward_u8(dsu_handle h, const uint8_t* color_dev, const uint8_t* pos_de
     DEVICE_GUARD(h);
     if ((rc = ensure_shape(h, B, H, W))) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    CUDA_TRY(ingest_u8(color_dev, pos_dev, edge_dev, B, H, W, h->buf_hi[SK0], h->buf_lo[SK0], h->buf_C[SK0],
-                       h->cfg.filters[0], st));
+    CUDA_TRY(ingest_u8(color_dev, pos_dev, edge_dev, B, H, W, h->buf_hi[SK0], h->buf_lo[SK0],
+                       h->f32_acts ? reinterpret_cast<float*>(h->buf_hi[SK0]) : nullptr, h->buf_C[SK0], h->cfg.filters[0], st));
     return run_network(h, B, H, W, y_dev, out_rgba_dev, color_dev + 3, 4, st);
 }
 
@@ -1131,6 +1315,16 @@ int dsu_pos2edge(const uint8_t* pos_dev, int32_t B, int32_t H, int32_t W, uint8_
     if (!pos_dev || !edge_dev || B <= 0 || H <= 0 || W <= 0) return fail(DSU_E_INVALID, "bad argument");
     CUDA_TRY(pos2edge(pos_dev, B, H, W, edge_dev, static_cast<cudaStream_t>(stream)));
     return DSU_OK;
+}
+
+int dsu_debug_watchdog(dsu_handle h, uint64_t* out, int32_t n) {
+    if (!h || !out) return fail(DSU_E_INVALID, "null argument");
+    int found = 0;
+    for (int i = 0; i < n; ++i) {
+        out[i] = (h->wd_host && i < 32) ? h->wd_host[i] : 0;
+        if (out[i]) ++found;
+    }
+    return found;
 }
 
 int dsu_debug_read(dsu_handle h, int32_t buffer, int32_t plane, void* dst_host, size_t bytes) {

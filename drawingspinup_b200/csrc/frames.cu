@@ -35,8 +35,14 @@ __device__ __forceinline__ float norm_u8(uint8_t v) {
     return __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(v), 255.0f), 0.5f), 0.5f);
 }
 
+// 8 fp32 values -> fp32 NHWC (stage 1 of the split-fp16 mode keeps fp32 activations)
+__device__ __forceinline__ void store8_f32(float* dst, const float* v) {
+    reinterpret_cast<float4*>(dst)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(dst)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+
 __global__ void ingest_f32_kernel(const float* __restrict__ x, int cin, int cpad, size_t npix_frame, size_t npix,
-                                  __half* hi, __half* lo, int pitch, int choff) {
+                                  __half* hi, __half* lo, float* f32, int pitch, int choff) {
     const size_t p = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
     if (p >= npix) return;
     const size_t n = p / npix_frame, q = p % npix_frame;
@@ -45,13 +51,14 @@ __global__ void ingest_f32_kernel(const float* __restrict__ x, int cin, int cpad
         float v[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) v[c] = (g + c < cin) ? xp[static_cast<size_t>(g + c) * npix_frame] : 0.0f;
-        store8(hi + p * pitch + choff + g, lo ? lo + p * pitch + choff + g : nullptr, v);
+        if (f32) store8_f32(f32 + p * pitch + choff + g, v);
+        else store8(hi + p * pitch + choff + g, lo ? lo + p * pitch + choff + g : nullptr, v);
     }
 }
 
 __global__ void ingest_u8_kernel(const uchar4* __restrict__ color, const uchar4* __restrict__ pos,
                                  const uint8_t* __restrict__ edge, size_t npix,
-                                 __half* hi, __half* lo, int pitch, int choff) {
+                                 __half* hi, __half* lo, float* f32, int pitch, int choff) {
     const size_t p = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
     if (p >= npix) return;
     uchar4 c = color[p];
@@ -59,7 +66,8 @@ __global__ void ingest_u8_kernel(const uchar4* __restrict__ color, const uchar4*
     const float mask = __fdiv_rn(static_cast<float>(c.w), 255.0f);      // alpha BEFORE the edge burn-in (data.py:28)
     if (edge && edge[p] < 255) { c.x = 0; c.y = 0; c.z = 0; }           // overlap_edge_on_img
     float v[8] = {norm_u8(c.x), norm_u8(c.y), norm_u8(c.z), mask, norm_u8(q.x), norm_u8(q.y), 0.0f, 0.0f};
-    store8(hi + p * pitch + choff, lo ? lo + p * pitch + choff : nullptr, v);
+    if (f32) store8_f32(f32 + p * pitch + choff, v);
+    else store8(hi + p * pitch + choff, lo ? lo + p * pitch + choff : nullptr, v);
 }
 
 __global__ void frames_to_tensor_kernel(const uchar4* __restrict__ color, const uchar4* __restrict__ pos,
@@ -117,6 +125,34 @@ __global__ void maxpool2_kernel(const __half* __restrict__ in_hi, const __half* 
         ol.x = pack_h2f(bl[0], bl[1]); ol.y = pack_h2f(bl[2], bl[3]); ol.z = pack_h2f(bl[4], bl[5]); ol.w = pack_h2f(bl[6], bl[7]);
         *reinterpret_cast<uint4*>(out_lo + op * out_pitch + g * 8) = ol;
     }
+}
+
+// the same pool over fp32 NHWC (4 channels per thread)
+__global__ void maxpool2_f32_kernel(const float* __restrict__ in, int in_pitch, int in_choff, int B, int Hin, int Win, int C,
+                                    float* out, int out_pitch) {
+    const int Ho = Hin / 2, Wo = Win / 2, G = C / 4;
+    const size_t total = static_cast<size_t>(B) * Ho * Wo * G;
+    const size_t t = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (t >= total) return;
+    const int g = static_cast<int>(t % G);
+    const size_t op = t / G;
+    const int ox = static_cast<int>(op % Wo);
+    const int oy = static_cast<int>((op / Wo) % Ho);
+    const int n = static_cast<int>(op / (static_cast<size_t>(Wo) * Ho));
+    float4 best = make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const size_t ip = (static_cast<size_t>(n) * Hin + 2 * oy + (k >> 1)) * Win + 2 * ox + (k & 1);
+        const float4 v = *reinterpret_cast<const float4*>(in + ip * in_pitch + in_choff + g * 4);
+        if (k == 0) best = v;
+        else {      // strict > keeps the first maximum, like the fp16 kernel above and F.max_pool2d's value
+            if (v.x > best.x) best.x = v.x;
+            if (v.y > best.y) best.y = v.y;
+            if (v.z > best.z) best.z = v.z;
+            if (v.w > best.w) best.w = v.w;
+        }
+    }
+    *reinterpret_cast<float4*>(out + op * out_pitch + g * 4) = best;
 }
 
 __device__ __forceinline__ uint8_t to_u8_dev(float x) {
@@ -240,17 +276,17 @@ inline unsigned blocks_for(size_t n, int threads) { return static_cast<unsigned>
 
 }  // namespace
 
-cudaError_t ingest_f32(const float* x, int B, int cin, int cpad, int H, int W, __half* hi, __half* lo, int pitch,
+cudaError_t ingest_f32(const float* x, int B, int cin, int cpad, int H, int W, __half* hi, __half* lo, float* f32, int pitch,
                        int choff, cudaStream_t st) {
     const size_t npf = static_cast<size_t>(H) * W, np = npf * B;
-    ingest_f32_kernel<<<blocks_for(np, 256), 256, 0, st>>>(x, cin, cpad, npf, np, hi, lo, pitch, choff);
+    ingest_f32_kernel<<<blocks_for(np, 256), 256, 0, st>>>(x, cin, cpad, npf, np, hi, lo, f32, pitch, choff);
     return cudaGetLastError();
 }
 cudaError_t ingest_u8(const uint8_t* color, const uint8_t* pos, const uint8_t* edge, int B, int H, int W,
-                      __half* hi, __half* lo, int pitch, int choff, cudaStream_t st) {
+                      __half* hi, __half* lo, float* f32, int pitch, int choff, cudaStream_t st) {
     const size_t np = static_cast<size_t>(H) * W * B;
     ingest_u8_kernel<<<blocks_for(np, 256), 256, 0, st>>>(reinterpret_cast<const uchar4*>(color),
-                                                          reinterpret_cast<const uchar4*>(pos), edge, np, hi, lo, pitch, choff);
+                                                          reinterpret_cast<const uchar4*>(pos), edge, np, hi, lo, f32, pitch, choff);
     return cudaGetLastError();
 }
 cudaError_t frames_to_tensor(const uint8_t* color, const uint8_t* pos, const uint8_t* edge, int B, int H, int W,
@@ -264,6 +300,12 @@ cudaError_t maxpool2(const __half* in_hi, const __half* in_lo, int in_pitch, int
                      __half* out_hi, __half* out_lo, int out_pitch, cudaStream_t st) {
     const size_t total = static_cast<size_t>(B) * (Hin / 2) * (Win / 2) * (C / 8);
     maxpool2_kernel<<<blocks_for(total, 256), 256, 0, st>>>(in_hi, in_lo, in_pitch, in_choff, B, Hin, Win, C, out_hi, out_lo, out_pitch);
+    return cudaGetLastError();
+}
+cudaError_t maxpool2_f32(const float* in, int in_pitch, int in_choff, int B, int Hin, int Win, int C, float* out, int out_pitch,
+                         cudaStream_t st) {
+    const size_t total = static_cast<size_t>(B) * (Hin / 2) * (Win / 2) * (C / 4);
+    maxpool2_f32_kernel<<<blocks_for(total, 256), 256, 0, st>>>(in, in_pitch, in_choff, B, Hin, Win, C, out, out_pitch);
     return cudaGetLastError();
 }
 cudaError_t ric_expand(const __half* src_hi, const __half* src_lo, int pitch, int choff, int groups, int B, int H, int W,

@@ -122,6 +122,43 @@ __device__ __forceinline__ uint4 ldg128_if(const void* ptr, bool ok) {
     return v;
 }
 
+// ---------------------------------------------------------------- TMA tensor loads (UTMALDG)
+// 4-D tiled tensor load global -> shared (coordinates innermost first: channel, x, y, frame); out-of-bounds elements
+// (negative or past the tensor's extent, per dimension) are written as zeros; completion in bytes on an mbarrier.
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
+// ---------------------------------------------------------------- tcgen05 with the A operand in tensor memory
+// D[tmem] += A[tmem] * B[smem desc]; kind::f16.  A[m][k] lives in lane m, column k/2, half k%2 (tools/umma_ts_probe.cu).
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// registers -> TMEM: this warp's 32 lanes x N consecutive 32-bit columns (warp w may only touch lanes 32*(w%4)..+31)
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t a, uint32_t b) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void tmem_st_zero32(uint32_t taddr) {
+    asm volatile(
+        "{\n\t.reg .b32 z;\n\tmov.b32 z, 0;\n\t"
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{z, z, z, z, z, z, z, z, z, z, z, z, z, z, z, z, z, z, z, z, z, z, z, z, z, z, z, z, z, z, z, z};\n\t}"
+        ::"r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle:
 // rows of 128 B (64 fp16), 8-row groups `sbo_bytes` apart.

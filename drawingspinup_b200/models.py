@@ -312,6 +312,15 @@ class _Generator(nn.Module):
             capi.check(n, "dsu_profile_forward")
         return [(capi.lib().dsu_step_name(handle, i).decode(), ms[i], fl[i]) for i in range(min(n, cap))]
 
+    def watchdog_records(self):
+        """Test hook: decoded watchdog records of the tensor-memory RIC kernel (see dsu_debug_watchdog): list of
+        (warp, tag, a, b, block) for every warp that timed out in a barrier wait."""
+        if not self._handle:
+            return []
+        buf = (C.c_uint64 * 32)()
+        capi.lib().dsu_debug_watchdog(self._handle, buf, 32)
+        return [(i, (v >> 48) & 0xFF, (v >> 32) & 0xFFFF, (v >> 16) & 0xFFFF, v & 0xFFFF) for i, v in enumerate(buf) if v]
+
     def debug_buffer(self, buffer: int, plane: int, shape, dtype=torch.float16) -> torch.Tensor:
         """Test hook: host copy of an internal activation buffer (see dsu_debug_read)."""
         t = torch.empty(shape, dtype=dtype)

@@ -137,6 +137,11 @@ int dsu_compose_rgba(const float* y_dev, const float* mask_dev, int32_t B, int32
 /* pos2edge (run_render.py:31-57): pos RGBA [B,H,W,4] -> edge [B,H,W] (255 on edges). */
 int dsu_pos2edge(const uint8_t* pos_dev, int32_t B, int32_t H, int32_t W, uint8_t* edge_dev, void* stream);
 
+/* Test hook: watchdog records of the tensor-memory RIC kernel (conv_ric_tm.cu).  A barrier wait that exceeds ~1 s (a
+ * protocol bug) stores 0xD5<<56 | tag<<48 | a<<32 | b<<16 | block per warp in pinned host memory and traps; this copies the
+ * first n slots (readable even after the launch failure) and returns how many are non-zero. */
+int dsu_debug_watchdog(dsu_handle h, uint64_t* out, int32_t n);
+
 /* Test hook: copy an internal activation buffer of the last forward to the host (synchronous).
  * buffer: 0 SK0(o0|x) 1 P0 2 O1 3 P1 4 O2 5 T 6 U 7 V2 8 V1 9 C11 10 S0 (fp16 NHWC), 100 = fp32 residual
  * stream; plane 0 = hi, 1 = lo (DSU_PREC_FP16X3 only).  Copies min(bytes, buffer size). */

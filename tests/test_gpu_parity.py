@@ -197,6 +197,38 @@ def test_reference_on_gpu_agrees_with_cpu_oracle(dev):
         assert (y - ref).abs().max().item() < 2e-5
 
 
+# ------------------------------------------------------------------ the round-1 RIC kernels stay covered (DSU_RIC_TM=0)
+@pytest.mark.parametrize("precision,tol", [("fp16x3", TOL), ("fp16", TOL_FP16)])
+@pytest.mark.parametrize("persist", [2, 0])
+def test_round1_ric_kernels_still_match_oracle(dev, monkeypatch, precision, tol, persist):
+    """Stage 1 normally runs the tensor-memory kernel (conv_ric_tm.cu).  DSU_RIC_TM=0 at create time selects the round-1
+    path - persistent RIC kernel (ric_persist=2) or the non-persistent one (0), tap expansion / fused first layer - which
+    remains the fallback for layers wider than the TMEM budget; both must keep meeting the same bounds."""
+    monkeypatch.setenv("DSU_RIC_TM", "0")
+    m, sd = _model(1, dev, precision=precision)
+    x = _frames_tensor(2, 40, 56, seed=19, stage=1)
+    m.set_knob("ric_persist", persist, device=dev)
+    with torch.no_grad():
+        y = m(x.to(dev)).cpu()
+    assert (y - _oracle(1, sd, x)).abs().max().item() < tol
+
+
+def test_tensor_memory_kernel_issuer_and_stage_knobs(dev):
+    """The tensor-memory RIC kernel with 1 / 3 issuing warps and the minimum weight ring gives the same result as the default
+    configuration up to fp32 accumulation order (several warps accumulate into one TMEM accumulator)."""
+    m, sd = _model(1, dev)
+    x = _frames_tensor(2, 72, 100, seed=23, stage=1).to(dev)
+    ref = _oracle(1, sd, x.cpu())
+    with torch.no_grad():
+        y0 = m(x).cpu()
+        for ni, sb in ((1, 2), (3, 2), (6, 4)):
+            m.set_knob("tm_ni", ni)
+            m.set_knob("tm_sb", sb)
+            y = m(x).cpu()
+            assert (y - y0).abs().max().item() < 1e-4
+            assert (y - ref).abs().max().item() < TOL
+
+
 # ------------------------------------------------------------------ size-independent properties at full size
 @pytest.mark.parametrize("stage", [1, 2])
 def test_batch_invariance_and_determinism_512(dev, stage):
@@ -394,8 +426,8 @@ def test_flop_model_and_launch_count(dev):
     assert abs(m1.algorithmic_flops(1, 512, 512) - 297.56e9) / 297.56e9 < 1e-3
     assert abs(m2.algorithmic_flops(1, 512, 512) - 543.72e9) / 543.72e9 < 1e-3
     # ingest + fused convs (+ RIC tap expansion of the input and 2 max-pools in stage 1; its dead smoother conv is not launched)
-    # stage 1 fp16x3: conv0 = tap expansion + contraction (2 launches); stage 2: each nearest-x2 up-convolution is four sub-pixel launches
-    assert m1.kernel_launches(1, 512, 512) == 1 + 21 + 3 and m2.kernel_launches(1, 512, 512) == 1 + 22 + 6
+    # stage 1: ingest + 21 fused convolutions + 2 max-pools; stage 2: each nearest-x2 up-convolution is four sub-pixel launches
+    assert m1.kernel_launches(1, 512, 512) == 1 + 21 + 2 and m2.kernel_launches(1, 512, 512) == 1 + 22 + 6
 
 
 def test_profile_hook_reports_every_launch(dev):
@@ -408,7 +440,7 @@ def test_profile_hook_reports_every_launch(dev):
         rows = m.profile_layers(1, 64, 64, reps=1)
         assert len(rows) == m.kernel_launches(1, 64, 64) - 1
         names = [r[0] for r in rows]
-        assert names[-1] == "conv_11_a.3" and any(n.startswith("upconv1") for n in names) and ("ric_expand" in names) == (stage == 1)
+        assert names[-1] == "conv_11_a.3" and any(n.startswith("upconv1") for n in names) and ("maxpool" in names) == (stage == 1)
         assert all(ms > 0 for _, ms, _ in rows)
         assert abs(sum(f for _, _, f in rows) - m.algorithmic_flops(1, 64, 64)) / m.algorithmic_flops(1, 64, 64) < 1e-6
 
