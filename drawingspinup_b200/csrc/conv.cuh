@@ -17,10 +17,8 @@ constexpr int kWorkers = 256;   // producer / epilogue threads (warps 0-7)
 // 32/64-cycle execution time of an M=128, N=64/128, K=16 MMA, so a CTA runs several issuing warps, each
 // with its own TMEM accumulator (sub-tile and/or K split; partial sums are added in the epilogue).
 constexpr int kIssuersTap = 1;   // tap-mode plain conv
-constexpr int kIssuersRic = 3;   // RIC: taps t with t % 3 == issuer
 constexpr int kIssuersHalo = 4;  // halo: ns sub-tiles x ks K-splits <= 4 (8 issuers with 4 worker warps measured slower)
 constexpr int kThreadsTap = (8 + kIssuersTap + 1) * 32;
-constexpr int kThreadsRic = (8 + kIssuersRic + 1) * 32;
 constexpr int kThreadsHalo = (8 + kIssuersHalo + 1) * 32;
 constexpr int kMaxSeg = 6;      // concat segments (second half = lo planes in exact mode)
 constexpr int kMaxStagesA = 9;  // RIC keeps one A buffer per tap resident
@@ -110,7 +108,6 @@ struct ConvParams {
     // the launch is a 2x2 convolution over the LOW-resolution source with asymmetric padding (pad_y, pad_x) whose output
     // pixel (oy, ox) of the Hout x Wout grid lands at (2*oy + sub_py, 2*ox + sub_px) of the (2*Hout) x (2*Wout) output buffer
     int sub, sub_py, sub_px, pad_y, pad_x;
-    int raw_choff;          // conv_ric_first.cu (experimental): first channel of the raw network input inside seg[0]
 };
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -141,17 +138,15 @@ struct TmParams {
     int b_stage_bytes;      // Cout * 576: 9 taps x 2 parts x (Cout x 32 B no-swizzle tile)
     const uint8_t* wpack;   // [stage][tap][part][Cout x 32 B]
     unsigned long long* dbg;    // watchdog records (pinned host memory, one slot per warp) or null
+    unsigned long long* trace;  // development trace (knob tm_trace): 5 x 1024 (event, clock) records of CTA 0, or null
 };
 cudaError_t launch_conv_ric_tm(const TmParams& p, cudaStream_t stream);
 size_t conv_ric_tm_smem_bytes(int cout, int sb);
 
 cudaError_t launch_conv(const ConvParams& p, cudaStream_t stream);
-cudaError_t launch_conv_halo(const ConvParams& p, cudaStream_t stream);
 cudaError_t launch_conv_halo_persist(const ConvParams& p, cudaStream_t stream);
-cudaError_t launch_conv_ric_persist(const ConvParams& p, cudaStream_t stream);
 // first-layer kernel (conv_first.cu): reuses sa = halo buffers, ks = issuers, ns = accumulator sets, ksize / pad / halo_rows / halo_bytes
 cudaError_t launch_conv_first(const ConvParams& p, cudaStream_t stream);
-cudaError_t launch_conv_ric_first(const ConvParams& p, cudaStream_t stream);   // experimental, DSU_RIC_FIRST=1
 size_t conv_halo_smem_bytes(const ConvParams& p);
 size_t conv_smem_bytes(const ConvParams& p);
 

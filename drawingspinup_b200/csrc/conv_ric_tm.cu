@@ -52,14 +52,37 @@ __device__ __noinline__ void tm_watchdog_fire(unsigned long long* dbg, uint32_t 
         __threadfence_system();
     }
 }
+// kSleepNs = 0: tight poll (the waits on the producer <-> MMA critical path).  kSleepNs > 0: test, then sleep between polls -
+// the waits of the roles that idle for most of a tile (epilogue, loaders, issuers).  The first version polled everything
+// with the blocking try_wait: NANOSLEEP.SYNCS wakes on every barrier event of the CTA, the idle roles re-tested ~170 times
+// per tile and three quarters of all issued instructions were wait loops competing with the producers for issue slots
+// (profiles/r02d_tm_upconv1_fp16 source page).
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+template <int kSleepNs>
 __device__ __forceinline__ void mbar_wait_wd(uint32_t bar, uint32_t parity, unsigned long long* dbg, uint32_t tag, int a, int b) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    if (mbar_test(bar, parity)) return;
+    long long t0 = 0;
+    uint32_t iter = 0;
     bool reported = false;
-    while (!mbar_try_wait(bar, parity)) {
-        const long long dt = clock64() - t0;
-        if (!reported && dt > 2000000000LL) { tm_watchdog_fire(dbg, tag, a, b); reported = true; }
-        if (dt > 2800000000LL) __trap();
+    while (true) {
+        if constexpr (kSleepNs > 0) {
+            asm volatile("nanosleep.u32 %0;" ::"n"(kSleepNs));
+            if (mbar_test(bar, parity)) return;
+        } else {
+            if (mbar_try_wait(bar, parity)) return;
+        }
+        if ((++iter & 0x3FFu) == 0) {                 // the clock is only read every 1024 polls
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            const long long dt = now - t0;
+            if (!reported && dt > 2000000000LL) { tm_watchdog_fire(dbg, tag, a, b); reported = true; }
+            if (dt > 2800000000LL) __trap();
+        }
     }
 }
 
@@ -67,6 +90,27 @@ template <int kRegs>
 __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 template <int kRegs>
 __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+
+// Development trace (knob tm_trace): CTA 0 records (event, clock64) pairs of one warp per role into pinned host memory,
+// 1024 slots per role: [0] producer warp 0, [1] issuer 0, [2] epilogue warp 0, [3] weight loader, [4] halo loader.
+struct Trace {
+    unsigned long long* p = nullptr;
+    int n = 0;
+    __device__ __forceinline__ void init(unsigned long long* base, int role, bool on) { p = on && base ? base + role * 1024 : nullptr; }
+    __device__ __forceinline__ void ev(int id, int a) {
+        if (p && n < 1024) { p[n++] = static_cast<unsigned long long>(id) << 56 | static_cast<unsigned long long>(a & 0xFFFF) << 40 |
+                                      (static_cast<unsigned long long>(clock64()) & 0xFFFFFFFFFFull); }
+    }
+};
+
+// position in a ring of n barriers / buffers and the parity of the current round (no divisions in the per-stage loops)
+struct Ring {
+    int idx = 0;
+    uint32_t phase = 0;
+    __device__ __forceinline__ void advance(int n) {
+        if (++idx == n) { idx = 0; phase ^= 1u; }
+    }
+};
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
@@ -122,6 +166,28 @@ __device__ __forceinline__ uint4 split4(float v0, float v1, float v2, float v3) 
     r.w = pack_h2(sub_half(v2, r.y, 0), sub_half(v3, r.y, 1));
     return r;
 }
+// packed fp32 pairs (FFMA2 / FMUL2, sm_100): two channels per instruction, the scalar weight is broadcast by the
+// instruction's operand selector (R.F32), so the fp32 blend costs 64 instead of 128 issue slots per 4-channel chunk
+__device__ __forceinline__ unsigned long long f2pack(uint32_t lo, uint32_t hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ unsigned long long f2bcast(float w) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(w));
+    return r;
+}
+__device__ __forceinline__ unsigned long long f2mul(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long f2fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
 template <int O>
 __device__ __forceinline__ void blend_f(const uint4 (&nb)[9], const float (&w)[8][4], uint4 (&out)[9]) {
     out[4] = split4(__uint_as_float(nb[4].x), __uint_as_float(nb[4].y), __uint_as_float(nb[4].z), __uint_as_float(nb[4].w));
@@ -132,13 +198,14 @@ __device__ __forceinline__ void blend_f(const uint4 (&nb)[9], const float (&w)[8
         const int m = (kq + O) & 7;
         const int r0 = tm_r0(m), c0 = tm_c0(m);
         const uint4 &a = nb[r0 * 3 + c0], &b = nb[r0 * 3 + c0 + 1], &c = nb[(r0 + 1) * 3 + c0], &d = nb[(r0 + 1) * 3 + c0 + 1];
-        float v[4];
-        const uint32_t* pa = &a.x; const uint32_t* pb = &b.x; const uint32_t* pc = &c.x; const uint32_t* pd = &d.x;
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            v[q] = fmaf(w[m][3], __uint_as_float(pd[q]), fmaf(w[m][2], __uint_as_float(pc[q]),
-                   fmaf(w[m][1], __uint_as_float(pb[q]), w[m][0] * __uint_as_float(pa[q]))));
-        out[t] = split4(v[0], v[1], v[2], v[3]);
+        // same operation order per channel as the scalar form: w00*a, then fma w01*b, w10*c, w11*d (each one rounding)
+        const unsigned long long w0 = f2bcast(w[m][0]), w1 = f2bcast(w[m][1]), w2 = f2bcast(w[m][2]), w3 = f2bcast(w[m][3]);
+        const unsigned long long v01 = f2fma(w3, f2pack(d.x, d.y), f2fma(w2, f2pack(c.x, c.y), f2fma(w1, f2pack(b.x, b.y), f2mul(w0, f2pack(a.x, a.y)))));
+        const unsigned long long v23 = f2fma(w3, f2pack(d.z, d.w), f2fma(w2, f2pack(c.z, c.w), f2fma(w1, f2pack(b.z, b.w), f2mul(w0, f2pack(a.z, a.w)))));
+        float v0, v1, v2, v3;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(v0), "=f"(v1) : "l"(v01));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(v2), "=f"(v3) : "l"(v23));
+        out[t] = split4(v0, v1, v2, v3);
     }
 }
 
@@ -219,6 +286,9 @@ conv_ric_tm_kernel(const __grid_constant__ TmParams P) {
         const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
         const uint32_t halo_u32 = base + L.halo0;
         int j = 0, gb = 0;                                           // stages / blocks produced so far by this CTA
+        Ring ra, rd;                                                 // A stage being written; completion barrier of step j - SA
+        Trace tr;
+        tr.init(P.trace, 0, blockIdx.x == 0 && tid == 0);
         for (int it = 0; it < my_tiles; ++it) {
             int n, ty0, tx0;
             tile_coords(it, n, ty0, tx0);
@@ -260,22 +330,36 @@ conv_ric_tm_kernel(const __grid_constant__ TmParams P) {
             for (int b = 0; b < P.nblocks; ++b, ++gb) {
                 const TmBlock blk = P.blk[b];
                 const int hb = gb & 1;
-                mbar_wait_wd(bar_halo_full + 8 * hb, (gb >> 1) & 1, P.dbg, 1, gb, it);
+                mbar_wait_wd<0>(bar_halo_full + 8 * hb, (gb >> 1) & 1, P.dbg, 1, gb, it);
                 const uint32_t hbase = halo_u32 + static_cast<uint32_t>(hb) * kTmHaloBytes;
                 for (int h = 0; h < blk.nstages; ++h, ++j) {
-                    const int slot = j % SA;
+                    const int slot = ra.idx;
                     if (j >= SA) {                                   // the MMAs that read this A stage last must be complete
-                        const int jp = j - SA;
-                        mbar_wait_wd(bar_done + 8 * (jp % SB), (jp / SB) & 1, P.dbg, 2, j, it);
+                        mbar_wait_wd<0>(bar_done + 8 * rd.idx, rd.phase, P.dbg, 2, j, it);
+                        rd.advance(SB);
                         tc_fence_after();
                     }
+                    ra.advance(SA);
+                    tr.ev(1, j);
                     const uint32_t col0 = a_col0 + static_cast<uint32_t>(slot * kTmStageCols);
                     const int nvalid = blk.chunks[h];
 #pragma unroll 1
                     for (int u = 0; u < 2; ++u) {
                         const int ci = 2 * g + u;                    // chunk of the stage; chunk of the line = 4 * h + ci
+                        if (ci >= nvalid) {                          // K padding of a ragged last stage: the MMA reads these columns
+                            if constexpr (!kExact) {
+                                const uint32_t cb = lane_addr + col0 + static_cast<uint32_t>((ci >> 1) * 72 + (ci & 1) * 4);
+#pragma unroll
+                                for (int t = 0; t < 9; ++t) tmem_st4(cb + t * 8, 0u, 0u, 0u, 0u);
+                            } else {
+                                const uint32_t cb = lane_addr + col0 + static_cast<uint32_t>(ci * 2);
+#pragma unroll
+                                for (int t = 0; t < 9; ++t) { tmem_st2(cb + t * 8, 0u, 0u); tmem_st2(cb + 72 + t * 8, 0u, 0u); }
+                            }
+                            continue;
+                        }
                         uint4 out[9];
-                        if (ci < nvalid) {
+                        {
                             const uint32_t cx = static_cast<uint32_t>(4 * h + ci) << 4;
                             uint4 nb[9];
 #pragma unroll
@@ -303,9 +387,6 @@ conv_ric_tm_kernel(const __grid_constant__ TmParams P) {
                                     default: blend_f<7>(nb, w, out); break;
                                 }
                             }
-                        } else {
-#pragma unroll
-                            for (int t = 0; t < 9; ++t) out[t] = make_uint4(0, 0, 0, 0);
                         }
                         __syncwarp();                                // reconverge before the warp-collective stores
                         if constexpr (!kExact) {
@@ -327,6 +408,7 @@ conv_ric_tm_kernel(const __grid_constant__ TmParams P) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_a_full + 8 * slot);
+                    tr.ev(2, j);
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_halo_empty + 8 * hb);    // this warp has read the halo tile for the last time
@@ -345,18 +427,26 @@ conv_ric_tm_kernel(const __grid_constant__ TmParams P) {
             tc_fence_before();
             mbar_arrive(bar_acc_empty + 8 * s);
         }
+        Ring rs;
+        Trace tr;
+        tr.init(P.trace, 2, blockIdx.x == 0 && tid == kWarpEpi0 * 32);
         for (int it = 0; it < my_tiles; ++it) {
             int n, ty0, tx0;
             tile_coords(it, n, ty0, tx0);
-            const int set = it % NSETS;
-            mbar_wait_wd(bar_acc_full + 8 * set, (it / NSETS) & 1, P.dbg, 3, it, set);
+            const int set = rs.idx;
+            mbar_wait_wd<256>(bar_acc_full + 8 * set, rs.phase, P.dbg, 3, it, set);
+            tr.ev(5, it);
+            rs.advance(NSETS);
             tc_fence_after();
             const uint32_t t_acc = lane_addr + static_cast<uint32_t>(set * C);
-            epilogue_row<kEpiAll>(p, s_par, t_acc, n, ty0 + (r >> 4), tx0 + (r & 15), 0, 1, 0, 1);
+            // stage 1 only needs the plain variants (no activation / ReLU / LeakyReLU; never a second affine or a lo plane)
+            epilogue_row<0x0007u>(p, s_par, t_acc, n, ty0 + (r >> 4), tx0 + (r & 15), 0, 1, 0, 1);
+            tr.ev(8, it);
             for (int c = 0; c < C; c += 32) tmem_st_zero32(t_acc + c);
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(bar_acc_empty + 8 * set);
+            tr.ev(6, it);
         }
     } else {
         reg_dec<40>();
@@ -367,21 +457,28 @@ conv_ric_tm_kernel(const __grid_constant__ TmParams P) {
                 const uint32_t idesc = umma_idesc_f16(kTileM, C);
                 const uint32_t tile_b = static_cast<uint32_t>(C) * 32u;          // one (tap, part) weight tile
                 int j = 0;
+                Ring rs, ra, rb;
+                Trace tr;
+                tr.init(P.trace, 1, blockIdx.x == 0 && tid == kWarpIss0 * 32);
                 for (int it = 0; it < my_tiles; ++it) {
-                    const int set = it % NSETS;
-                    mbar_wait_wd(bar_acc_empty + 8 * set, (it / NSETS) & 1, P.dbg, 4, it, set);        // drained and zeroed
+                    const int set = rs.idx;
+                    mbar_wait_wd<96>(bar_acc_empty + 8 * set, rs.phase, P.dbg, 4, it, set);        // drained and zeroed
+                    rs.advance(NSETS);
                     tc_fence_after();
                     const uint32_t d_addr = tmem_base + static_cast<uint32_t>(set * C);
                     for (int b = 0; b < P.nblocks; ++b) {
                         const TmBlock blk = P.blk[b];
                         for (int h = 0; h < blk.nstages; ++h, ++j) {
-                            const int slot = j % SA, sb = j % SB;
+                            const int slot = ra.idx, sb = rb.idx;
                             // fp16: parts = live K16 steps (2 chunks each); split-fp16: hi*Whi, lo*Whi, hi*Wlo of one K16 step
                             const int nparts = kExact ? 3 : (blk.chunks[h] + 1) >> 1;
                             const int nq = 9 * nparts;
-                            mbar_wait_wd(bar_b_full + 8 * sb, (j / SB) & 1, P.dbg, 5, j, it);
-                            mbar_wait_wd(bar_a_full + 8 * slot, (j / SA) & 1, P.dbg, 6, j, it);
+                            mbar_wait_wd<32>(bar_b_full + 8 * sb, rb.phase, P.dbg, 5, j, it);
+                            mbar_wait_wd<32>(bar_a_full + 8 * slot, ra.phase, P.dbg, 6, j, it);
+                            ra.advance(SA);
+                            rb.advance(SB);
                             tc_fence_after();
+                            tr.ev(3, j);
                             const uint32_t a_stage = tmem_base + a_col0 + static_cast<uint32_t>(slot * kTmStageCols);
                             const uint32_t b_stage = base + L.b0 + static_cast<uint32_t>(sb) * P.b_stage_bytes;
                             for (int q = wi; q < nq; q += NI) {
@@ -394,6 +491,7 @@ conv_ric_tm_kernel(const __grid_constant__ TmParams P) {
                             }
                             if (elect_one()) umma_commit(bar_done + 8 * sb);     // frees the A stage (producers) and the weight stage (loader)
                             __syncwarp();
+                            tr.ev(4, j);
                         }
                     }
                     if (elect_one()) umma_commit(bar_acc_full + 8 * set);
@@ -411,7 +509,7 @@ conv_ric_tm_kernel(const __grid_constant__ TmParams P) {
                 const int sy0 = (ty0 - 1) >> p.up, sx0 = (tx0 - 1) >> p.up;
                 for (int b = 0; b < P.nblocks; ++b, ++gb) {
                     const int hb = gb & 1;
-                    if (gb >= 2) mbar_wait_wd(bar_halo_empty + 8 * hb, ((gb >> 1) - 1) & 1, P.dbg, 7, gb, it);
+                    if (gb >= 2) mbar_wait_wd<160>(bar_halo_empty + 8 * hb, ((gb >> 1) - 1) & 1, P.dbg, 7, gb, it);
                     if (elect_one()) {
                         const TmBlock blk = P.blk[b];
                         mbar_arrive_expect_tx(bar_halo_full + 8 * hb, box_bytes);
@@ -424,10 +522,15 @@ conv_ric_tm_kernel(const __grid_constant__ TmParams P) {
         } else {
             // ============================================================ weight loader: one bulk copy per stage
             int j = 0;
+            Ring rb;
+            Trace tr;
+            tr.init(P.trace, 3, blockIdx.x == 0 && lane == 0);
             for (int it = 0; it < my_tiles; ++it)
                 for (int s = 0; s < P.nstages; ++s, ++j) {
-                    const int sb = j % SB;
-                    if (j >= SB) mbar_wait_wd(bar_done + 8 * sb, ((j / SB) - 1) & 1, P.dbg, 8, j, it);
+                    const int sb = rb.idx;
+                    if (j >= SB) mbar_wait_wd<160>(bar_done + 8 * sb, rb.phase ^ 1u, P.dbg, 8, j, it);
+                    rb.advance(SB);
+                    tr.ev(7, j);
                     if (elect_one()) {
                         mbar_arrive_expect_tx(bar_b_full + 8 * sb, static_cast<uint32_t>(P.b_stage_bytes));
                         bulk_g2s(base + L.b0 + static_cast<uint32_t>(sb) * P.b_stage_bytes, P.wpack + static_cast<size_t>(s) * P.b_stage_bytes,

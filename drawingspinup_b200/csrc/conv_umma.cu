@@ -6,11 +6,8 @@
 //     per output pixel.  Each 16-byte slot of a row is 8 channels of one tap of one concat
 //     segment (slot table), so plain 3x3 / 7x7 taps, stride 2, fused nearest-x2 upsampling and
 //     channel concatenation are pure address arithmetic (cp.async with zero fill at the border).
-//   * RIC mode (stage-1 rotation-invariant deformable conv, models.py:302-351): a thread loads the
-//     3x3 neighbourhood of its pixel once (9 x 16 B, zero outside the image) and blends all 8
-//     non-centre taps from it - every tap samples on the unit circle around the pixel - writing one
-//     A buffer per tap.  Taps are visited in octant-rotated order so the 2x2 corner set of each
-//     tap is a compile-time constant (no dynamic register indexing).
+//     (Used for the stride-2 convolutions of stage 2 and as the generic fallback of its first layer; the stride-1 layers run
+//     the halo-reuse kernel, stage 1 the tensor-memory RIC kernel conv_ric_tm.cu.)
 //   * warp 9 streams the pre-swizzled weight tile (B operand) with 1-D bulk async copies.
 //   * warp 8 issues tcgen05.mma (one thread) and commits stage-release / accumulator-ready
 //     mbarriers.
@@ -21,7 +18,6 @@
 // 128-byte row; A steps 0-3 are issued against B steps 0,1,0,1 and A steps 0,1 again against B steps 2,3 into the
 // same accumulator: a_hi*W_hi + a_lo*W_hi + a_hi*W_lo, fp32-grade products at 3x the tensor work.
 #include "conv_device.cuh"
-#include "ric_producer.cuh"
 
 namespace dsu {
 
@@ -47,11 +43,8 @@ __host__ __device__ inline SmemLayout smem_layout(int sa, int sb, int b_bytes, i
 
 }  // namespace
 
-// kMode: 0 = tap-mode plain conv, 1 = RIC (fp16, fp32 blend), 2 = RIC (split fp16 hi|lo), 3 = RIC (fp16, packed half2 blend)
-template <int kMode>
-__global__ void __launch_bounds__(kMode ? kThreadsRic : kThreadsTap, kMode ? 1 : 2)
+__global__ void __launch_bounds__(kThreadsTap, 2)
 conv_umma_kernel(const __grid_constant__ ConvParams p) {
-    constexpr bool kRic = kMode != 0;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_u32 = smem_u32(smem_raw);
     const uint32_t base = (raw_u32 + 1023u) & ~1023u;
@@ -78,14 +71,14 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
     if (warp == 8) {
         if (lane == 0) {
             for (int s = 0; s < SA; ++s) {
-                mbar_init(bar_full_a + 8 * s, kRic ? kWorkers / 32 : kWorkers);   // RIC producers arrive once per warp
+                mbar_init(bar_full_a + 8 * s, kWorkers);
                 mbar_init(bar_empty_a + 8 * s, 1);
             }
             for (int s = 0; s < SB; ++s) {
                 mbar_init(bar_full_b + 8 * s, 1);
                 mbar_init(bar_empty_b + 8 * s, 1);
             }
-            mbar_init(bar_accum, kRic ? p.ks : 1);
+            mbar_init(bar_accum, 1);
             fence_mbar_init();
         }
         __syncwarp();
@@ -106,7 +99,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         const int swz = prow & 7;       // (row & 7) of all of this thread's rows
         const size_t frame_in = static_cast<size_t>(n) * p.Hin * p.Win;
 
-        if constexpr (!kRic) {
+        {
             // ---- plain taps: cp.async (LDGSTS) with zero fill, completion lagging by LAG chunks
             const uint32_t row_off = static_cast<uint32_t>(prow) * 128u + (static_cast<uint32_t>(j ^ swz) << 4);
             const int ox = tx0 + (prow & 15);
@@ -142,9 +135,6 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             fence_proxy_async_smem();
             for (int q = (p.nchunks > LAG ? p.nchunks - LAG : 0); q < p.nchunks; ++q)
                 mbar_arrive(bar_full_a + 8 * (q % SA));
-        } else {
-            // ---- RIC: 3x3 neighbourhood -> 8 blended circle taps + centre, one A buffer per tap (ric_producer.cuh)
-            ric_produce<kMode == 2, kMode == 3>(p, smem + L.a0, bar_full_a, bar_empty_a, tid, n, ty0, tx0);
         }
 
         // ======================================================== epilogue (warps 0-7)
@@ -153,11 +143,11 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         {
             const int quad = warp & 3;
             const int r = quad * 32 + lane;      // accumulator row = TMEM lane = patch pixel
-            epilogue_row<kMode == 0 ? kEpiAll : ((kMode == 2 ? 0x0702u : 0x0007u))>(p, s_par, tmem_base + (static_cast<uint32_t>(quad * 32) << 16), n, ty0 + (r >> 4), tx0 + (r & 15), warp >> 2,
-                         kRic ? p.ks : 1, C);
+            epilogue_row<kEpiAll>(p, s_par, tmem_base + (static_cast<uint32_t>(quad * 32) << 16), n, ty0 + (r >> 4), tx0 + (r & 15), warp >> 2,
+                         1, C);
         }
         tc_fence_before();
-    } else if (warp < 8 + (kRic ? kIssuersRic : kIssuersTap)) {   // (idle issuer warps fall through)
+    } else if (warp < 8 + kIssuersTap) {
         // ======================================================== MMA issuers
         // Warp-uniform loops (loop counters, launch constants) and one elected lane issues: keeps the
         // descriptors in uniform registers (a divergent single-lane loop makes the compiler wrap every
@@ -167,17 +157,16 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         // The number of RIC issuers (p.ks, 1..3) is chosen by the planner so that every issuer owns a private
         // weight ring of >= 2 stages: a ring shared by several consumers would let a warp that is one ring
         // revolution ahead pass mbarrier.try_wait.parity on the previous phase.
-        const int NI = kRic ? p.ks : 1;
+        const int NI = 1;
         const int SBK = SB / NI;
         const int wi = warp - 8;
         if (wi < NI) {
         const uint32_t idesc = umma_idesc_f16(kTileM, C);
         const uint32_t d_addr = tmem_base + static_cast<uint32_t>(wi * C);
-        const int tail_from = kRic ? (p.nblocks - 1) * 9 : p.nchunks - 1;
+        const int tail_from = p.nchunks - 1;
         uint32_t acc = 0;
         int cnt = 0;
         for (int q = 0; q < p.nchunks; ++q) {
-            if (kRic && (q % 9) % NI != wi) continue;
             const int s_a = q % SA;
             const int s_b = wi * SBK + cnt % SBK;
             const uint32_t b_par = (cnt / SBK) & 1;
@@ -222,17 +211,10 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         }
         tc_fence_before();
     } else {
-        // ======================================================== weight (B operand) loader: chunk q -> ring of its issuer
-        const int NI = kRic ? p.ks : 1;
-        const int SBK = SB / NI;
-        int cnt[kIssuersRic] = {0, 0, 0};
+        // ======================================================== weight (B operand) loader: chunk q -> stage q % SB
         for (int q = 0; q < p.nchunks; ++q) {
-            const int k = kRic ? (q % 9) % NI : 0;
-            int c = 0;
-#pragma unroll
-            for (int i = 0; i < kIssuersRic; ++i) if (i == k) { c = cnt[i]; cnt[i] = c + 1; }
-            const int s = k * SBK + c % SBK;
-            if (c >= SBK) mbar_wait(bar_empty_b + 8 * s, ((c / SBK) - 1) & 1);
+            const int s = q % SB;
+            if (q >= SB) mbar_wait(bar_empty_b + 8 * s, ((q / SB) - 1) & 1);
             if (elect_one()) {
                 mbar_arrive_expect_tx(bar_full_b + 8 * s, static_cast<uint32_t>(p.b_bytes));
                 bulk_g2s(base + L.b0 + s * p.b_bytes, p.wpack + static_cast<size_t>(q) * p.b_bytes,
@@ -258,24 +240,14 @@ cudaError_t launch_conv(const ConvParams& p, cudaStream_t stream) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 64 && !attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(conv_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(conv_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(conv_umma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_set[dev] = true;
     }
-    if (p.sa < 2 || p.sa > kMaxStagesA || p.sb < 2 || p.sb > kMaxStagesB || (p.ric && (p.sa != 9 || p.ks < 1 || p.ks > kIssuersRic || p.sb / p.ks < 2)) ||
-        conv_smem_bytes(p) > 227 * 1024)
+    if (p.ric || p.sa < 2 || p.sa > kMaxStagesA || p.sb < 2 || p.sb > kMaxStagesB || conv_smem_bytes(p) > 227 * 1024)
         return cudaErrorInvalidConfiguration;
     dim3 grid((p.Wout + kTileW - 1) / kTileW, (p.Hout + kTileH - 1) / kTileH, p.B);
-    if (p.ric && p.exact) conv_umma_kernel<2><<<grid, kThreadsRic, conv_smem_bytes(p), stream>>>(p);
-    else if (p.ric >= 2) conv_umma_kernel<3><<<grid, kThreadsRic, conv_smem_bytes(p), stream>>>(p);
-    else if (p.ric) conv_umma_kernel<1><<<grid, kThreadsRic, conv_smem_bytes(p), stream>>>(p);
-    else conv_umma_kernel<0><<<grid, kThreadsTap, conv_smem_bytes(p), stream>>>(p);
+    conv_umma_kernel<<<grid, kThreadsTap, conv_smem_bytes(p), stream>>>(p);
     return cudaGetLastError();
 }
 

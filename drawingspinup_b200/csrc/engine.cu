@@ -41,7 +41,7 @@ int fail(int code, const std::string& msg) {
             return fail(DSU_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));      \
     } while (0)
 
-enum BufId { SK0 = 0, P0, O1, P1, O2, TT, UU, V2, V1, C11, S0, EXP0, NBUF };
+enum BufId { SK0 = 0, P0, O1, P1, O2, TT, UU, V2, V1, C11, S0, NBUF };
 
 struct SegDef {
     int buf, choff, nch;   // buffer, first channel, channels consumed (multiple of 8)
@@ -55,15 +55,13 @@ struct LayerDef {
     int act = 0;
     int out_buf = -1, out_choff = 0, out_relu = 0, out2_buf = -1;
     int resid_in = 0, resid_out = 0, final = 0;
-    int halo = 0;          // plain stride-1 conv run by the halo-reuse kernel (conv_halo.cu)
-    int expanded = 0;      // stage-1 conv0: the 9 RIC taps were materialised by ric_expand -> 1x1 contraction
+    int halo = 0;          // plain stride-1 conv run by the halo-reuse kernel (conv_halo_persist.cu)
     int first = 0;         // one 8-channel group per tap, stride 1: im2col from a shared-memory halo (conv_first.cu)
     // experimental (DSU_SUBPIXEL=1): sub-pixel class py*2+px of a nearest-x2 + 3x3 convolution (models.py:180-192):
     // out(2y+py, 2x+px) = sum over a,b in {0,1} of Wc[a][b] * in(y+a-1+py, x+b-1+px), Wc = sums of the 3x3 taps that hit the
     // same source pixel - exact including the zero border, 4 taps instead of 9 per output pixel.  k = 2 for such a layer and
     // wk = 3 is the kernel size of the stored weights; -1 = ordinary layer
     int sub = -1, wk = 0;
-    int raw_buf = -1, raw_choff = 0;   // expanded stage-1 conv0: where the un-expanded 8-channel input lives (conv_ric_first.cu)
     // tensor-memory RIC kernel (conv_ric_tm.cu): channel runs (one TMA tensor map each), 128-byte blocks, packed weights
     int tm = 0;
     struct TmRun { int buf, choff, nch, wch0, wn; };
@@ -82,7 +80,7 @@ struct LayerDef {
 };
 
 struct Step {
-    int type;    // 0 conv, 1 maxpool, 2 RIC tap expansion of the network input
+    int type;    // 0 conv, 1 maxpool
     int layer;
     int src, src_choff, C, dst;
 };
@@ -90,24 +88,19 @@ struct Step {
 // Development knobs: read ONCE from the environment (DSU_<NAME>) by dsu_create, adjustable per handle through
 // dsu_set_knob (tests / tools); 0 = "planner decides" for the sizing knobs.  Defaults are the measured best.
 struct Knobs {
-    int ric_persist = 2;      // 0 never, 1 Cout <= 64, 2 all RIC layers run the persistent kernel
-    int ric_first = 1;        // stage-1 conv0 fused with its tap expansion (conv_ric_first.cu; fp16 mode)
-    int ric_fp32_blend = 0;   // fp16 mode: blend the RIC taps in fp32 instead of packed half2
-    int ric_ks = 0;
     int first = 1;            // GeneratorJ.conv0 in the im2col-free kernel (conv_first.cu); 0 = tap mode
     int first_ks = 0, first_na = 0, first_sets = 0;
     int halo_persist = 2, halo_ns = 0, halo_ks = 0, halo_na = 0, halo_sb = 0, halo_tps = 0;
     int subpixel = 1;         // plan-time: stage-2 nearest-x2 + 3x3 as four 2x2 sub-pixel convolutions
-    int ric_tm = 1;           // plan-time: stage 1 runs the tensor-memory RIC kernel (conv_ric_tm.cu); 0 = the round-1 kernels
     int tm_ni = 0, tm_sb = 0; // tensor-memory kernel: issuing warps / weight stages (0 = planner decides)
+    int tm_trace = 0;         // development: 1 + index of the launch step whose CTA 0 records an event trace (dsu_debug_watchdog slots 32..)
 };
 struct KnobName { const char* name; int Knobs::*field; };
 const KnobName kKnobNames[] = {
-    {"ric_persist", &Knobs::ric_persist}, {"ric_first", &Knobs::ric_first}, {"ric_fp32_blend", &Knobs::ric_fp32_blend},
-    {"ric_ks", &Knobs::ric_ks}, {"first", &Knobs::first}, {"first_ks", &Knobs::first_ks}, {"first_na", &Knobs::first_na},
+    {"first", &Knobs::first}, {"first_ks", &Knobs::first_ks}, {"first_na", &Knobs::first_na},
     {"first_sets", &Knobs::first_sets}, {"halo_persist", &Knobs::halo_persist}, {"halo_ns", &Knobs::halo_ns},
     {"halo_ks", &Knobs::halo_ks}, {"halo_na", &Knobs::halo_na}, {"halo_sb", &Knobs::halo_sb}, {"halo_tps", &Knobs::halo_tps},
-    {"subpixel", &Knobs::subpixel}, {"ric_tm", &Knobs::ric_tm}, {"tm_ni", &Knobs::tm_ni}, {"tm_sb", &Knobs::tm_sb},
+    {"subpixel", &Knobs::subpixel}, {"tm_ni", &Knobs::tm_ni}, {"tm_sb", &Knobs::tm_sb}, {"tm_trace", &Knobs::tm_trace},
 };
 Knobs knobs_from_env() {
     Knobs k;
@@ -236,7 +229,7 @@ int build_plan(dsu_engine* E) {
     setbuf(SK0, 0, f[0] + cp);
     setbuf(O1, 1, f[1]);
     setbuf(O2, 2, f[2]);
-    if (ric) { setbuf(P0, 1, f[0]); setbuf(P1, 2, f[1]); if (!E->ric_tm) setbuf(EXP0, 0, 9 * cp); }
+    if (ric) { setbuf(P0, 1, f[0]); setbuf(P1, 2, f[1]); }
     if (c.resnet_blocks > 0) { setbuf(TT, 2, f[2]); setbuf(UU, 2, f[2]); }
     setbuf(V2, 1, f[4]);
     setbuf(V1, 0, f[4]);
@@ -250,11 +243,6 @@ int build_plan(dsu_engine* E) {
         LayerDef L; L.name = "conv0"; L.wkey = "conv0.conv.weight"; L.bkey = bias_of("conv0.conv");
         L.bn = bn ? "conv0.normalization" : ""; L.k = k0; L.pad = k0 / 2; L.ric = ric; L.cout = f[0]; L.level_out = 0;
         L.segs = {{SK0, f[0], cp, 0, cin}}; L.act = 2; L.out_buf = SK0; L.out_choff = 0;
-        if (ric && !E->ric_tm) {   // round-1 path: sample the 9 taps of the 8-channel input once, then contract over 9 * cp channels
-            E->steps.push_back(Step{2, -1, SK0, f[0], cp, EXP0});
-            L.ric = 0; L.expanded = 1; L.segs = {{EXP0, 0, cp, 0, cin}};
-            L.raw_buf = SK0; L.raw_choff = f[0];
-        }
         add(L);
     }
     if (ric) E->steps.push_back(Step{1, -1, SK0, 0, f[0], P0});
@@ -331,8 +319,7 @@ int build_plan(dsu_engine* E) {
         L.segs = {{ric ? C11 : S0, 0, f[5], 0, f[5]}}; L.act = 1; L.final = 1;
         add(L);
     }
-    if (E->ric_tm)
-        for (LayerDef& L : E->layers) L.tm = L.ric ? 1 : 0;
+    for (LayerDef& L : E->layers) L.tm = L.ric ? 1 : 0;       // every stage-1 convolution runs the tensor-memory RIC kernel
     return DSU_OK;
 }
 
@@ -466,8 +453,8 @@ int compile_layer(dsu_engine* E, LayerDef& L) {
     if (L.sub >= 0) L.macs_per_px = real_k / 4.0 * 9.0 / 4.0 * C;
     auto dev_slot = [&](const HSlot& h, bool lo_plane) {
         Slot sl{};
-        sl.dy = static_cast<int8_t>(L.expanded ? 0 : h.kh - L.pad);
-        sl.dx = static_cast<int8_t>(L.expanded ? 0 : h.kw - L.pad);
+        sl.dy = static_cast<int8_t>(h.kh - L.pad);
+        sl.dx = static_cast<int8_t>(h.kw - L.pad);
         sl.seg = static_cast<uint8_t>(h.seg + (lo_plane ? kMaxSeg / 2 : 0));
         sl.valid = 1;
         sl.choff = static_cast<uint16_t>(h.choff);
@@ -482,23 +469,8 @@ int compile_layer(dsu_engine* E, LayerDef& L) {
     };
     // halo-reuse kernel: plain stride-1 convs with >= 32 channels per tap (the 8-channel 7x7 conv0 was measured slower
     // there: 49 single-K-step MMAs per tile; it has its own kernel, conv_first.cu, and the tap-mode kernel as fallback)
-    L.halo = (!L.ric && !L.expanded && L.stride == 1 && real_k / (k * k) >= 32) ? 1 : 0;
-    if (L.expanded) {
-        // data slot = (tap, 8-channel group) of the expanded buffer [pix][tap * nch + c]; weights keep their 3x3 index.
-        // Runs in the halo kernel as a 1x1 convolution: blocks of 8 data slots, one "tap" (chunk) per block.
-        L.halo = 1;
-        const SegDef& s0 = L.segs[0];
-        std::vector<HSlot> all;
-        for (int tap = 0; tap < k * k; ++tap)
-            for (int c8 = 0; c8 < s0.nch; c8 += 8)
-                all.push_back(HSlot{tap / k, tap % k, 0, tap * s0.nch + c8, s0.wch0 + c8, std::max(0, std::min(8, s0.wn - c8))});
-        for (size_t i = 0; i < all.size(); i += dpc) {
-            std::vector<HSlot> ds(all.begin() + i, all.begin() + std::min(all.size(), i + dpc));
-            push_dev_slots(ds);
-            chunks.push_back(ds);
-        }
-        L.nblocks = static_cast<int>(chunks.size());
-    } else if (!L.ric && !L.halo) {
+    L.halo = (!L.ric && L.stride == 1 && real_k / (k * k) >= 32) ? 1 : 0;
+    if (!L.ric && !L.halo) {
         // single 8-channel group per tap (conv0 of GeneratorJ), fp16 mode: one chunk per KERNEL ROW (slot j = tap (kh, j)),
         // the layout the im2col-free kernel (conv_first.cu) needs; the tap-mode kernel runs the same table
         L.first = (!exact && L.stride == 1 && L.up == 0 && L.segs.size() == 1 && L.segs[0].nch <= 8 && k > 3 && k <= 8 &&
@@ -771,7 +743,7 @@ int ensure_shape(dsu_engine* E, int B, int H, int W) {
             if (rc) return rc;
         }
     E->B = B; E->H = H; E->W = W;
-    if (E->ric_tm && (E->maps_B != B || E->maps_H != H || E->maps_W != W)) {
+    if (E->cfg.kind == DSU_KIND_GENERATORJ_RIC && (E->maps_B != B || E->maps_H != H || E->maps_W != W)) {
         int rc = build_tensor_maps(E, B, H, W);
         if (rc) return rc;
         E->maps_B = B; E->maps_H = H; E->maps_W = W;
@@ -779,14 +751,8 @@ int ensure_shape(dsu_engine* E, int B, int H, int W) {
     return DSU_OK;
 }
 
-// stage counts: plain conv shares one ring depth for A and B and aims at two CTAs per SM;
-// RIC keeps one A buffer per tap (9) and gives the rest of the SM's shared memory to the weight ring.
-void pick_stages(bool ric, int b_bytes, int* sa, int* sb) {
-    if (ric) {
-        *sa = 9;
-        *sb = std::max(2, std::min(kMaxStagesB, (227 * 1024 - 9 * kABytes - 8 * 1024) / b_bytes));
-        return;
-    }
+// stage counts of the tap-mode kernel: one ring depth for A and B, aiming at two CTAs per SM
+void pick_stages(int b_bytes, int* sa, int* sb) {
     const int stage = kABytes + b_bytes;
     int s = (108 * 1024) / stage;
     if (s < 2) s = (216 * 1024) / stage;
@@ -798,13 +764,6 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
                 int alpha_stride, cudaStream_t st, std::vector<cudaEvent_t>* evs = nullptr) {
     size_t step_idx = 0;
     const Knobs& K = E->knobs;
-    const int ric_persist_mode = K.ric_persist;
-    // stage-1 conv0 fused with its tap expansion (conv_ric_first.cu): fp16 mode, one 8-channel input group (2 weight chunks).
-    // ONE predicate decides both "skip the ric_expand step" and "launch the fused kernel" (a conv0 with 9..16 input channels
-    // keeps the expansion buffer and the halo kernel).
-    bool use_ric_first = false;
-    for (const LayerDef& L : E->layers)
-        if (L.expanded) use_ric_first = K.ric_first != 0 && !E->exact && L.raw_buf >= 0 && L.nchunks == 2;
     const int first_mode = K.first;
     for (const Step& sp : E->steps) {
         if (evs) CUDA_TRY(cudaEventRecord((*evs)[step_idx], st));
@@ -820,12 +779,6 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
                               E->buf_hi[sp.dst], E->buf_lo[sp.dst], E->buf_C[sp.dst], st));
             continue;
         }
-        if (sp.type == 2) {
-            if (use_ric_first) continue;      // the consumer samples the taps itself
-            CUDA_TRY(ric_expand(E->buf_hi[sp.src], E->buf_lo[sp.src], E->buf_C[sp.src], sp.src_choff, sp.C / 8, B, H, W,
-                                E->lv[0].lyx, E->lv[0].oct, E->buf_hi[sp.dst], E->buf_lo[sp.dst], st));
-            continue;
-        }
         const LayerDef& L = E->layers[sp.layer];
         ConvParams p{};
         // a sub-pixel class iterates over the low-resolution grid (one level below its output buffer)
@@ -835,18 +788,11 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
         p.Hin = H >> src_level; p.Win = W >> src_level;
         p.up = L.up; p.Hv = p.Hin << L.up; p.Wv = p.Win << L.up;
         p.stride = L.stride; p.ric = L.ric; p.exact = E->exact ? 1 : 0;
-        // fp16 mode blends the RIC taps with packed half2 math unless DSU_RIC_FP32_BLEND=1 (p.ric == 2 selects it)
-        if (L.ric && !E->exact && !K.ric_fp32_blend) p.ric = 2;
         p.nchunks = L.nchunks; p.nblocks = L.nblocks; p.Cout = L.cout;
         p.b_bytes = L.cout * 128;
         p.kmask_full = L.kmask_full; p.kmask_last = L.kmask_last; p.kmask2_full = L.kmask2_full; p.kmask2_last = L.kmask2_last;
-        pick_stages(L.ric != 0, p.b_bytes, &p.sa, &p.sb);
+        pick_stages(p.b_bytes, &p.sa, &p.sb);
         p.ks = 1;
-        if (L.ric) {   // K-split issuers: each needs a private weight ring of >= 2 stages and a TMEM accumulator
-            p.ks = std::max(1, std::min(kIssuersRic, std::min(p.sb / 2, 512 / L.cout)));
-            if (K.ric_ks > 0) p.ks = std::max(1, std::min(p.ks, K.ric_ks));
-            p.sb = (p.sb / p.ks) * p.ks;
-        }
         int cols = 32;
         while (cols < p.ks * L.cout) cols *= 2;
         p.tmem_cols = cols;
@@ -896,8 +842,8 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
             T.halo_w = L.up ? 10 : 18; T.halo_h = L.up ? 6 : 10;
             T.wpack = L.d_wpack_tm;
             if (!E->wd_host) {
-                if (cudaHostAlloc(reinterpret_cast<void**>(&E->wd_host), 32 * sizeof(unsigned long long), cudaHostAllocMapped) == cudaSuccess) {
-                    std::memset(E->wd_host, 0, 32 * sizeof(unsigned long long));
+                if (cudaHostAlloc(reinterpret_cast<void**>(&E->wd_host), (32 + 5 * 1024) * sizeof(unsigned long long), cudaHostAllocMapped) == cudaSuccess) {
+                    std::memset(E->wd_host, 0, (32 + 5 * 1024) * sizeof(unsigned long long));
                     if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&E->wd_dev), E->wd_host, 0) != cudaSuccess) E->wd_dev = nullptr;
                 } else {
                     E->wd_host = nullptr;
@@ -905,26 +851,14 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
                 }
             }
             T.dbg = E->wd_dev;
+            T.trace = (E->wd_dev && K.tm_trace > 0 && static_cast<size_t>(K.tm_trace) == step_idx) ? E->wd_dev + 32 : nullptr;
             CUDA_TRY(launch_conv_ric_tm(T, st));
-            continue;
-        }
-        if (L.expanded && use_ric_first) {
-            p.seg[0].ptr = E->buf_hi[L.raw_buf];
-            p.seg[0].pitch = E->buf_C[L.raw_buf];
-            p.raw_choff = L.raw_choff;
-            p.ric_lyx = E->lv[0].lyx; p.ric_oct = E->lv[0].oct;
-            p.sa = 4;
-            p.ns = 4 * L.cout <= 512 ? 4 : 2;
-            cols = 32;
-            while (cols < p.ns * L.cout) cols *= 2;
-            p.tmem_cols = cols;
-            CUDA_TRY(launch_conv_ric_first(p, st));
             continue;
         }
         if (L.halo) {
             // ns sub-tiles x ks K-split issuers (<= 4 issuing warps, <= 512 TMEM columns); shared memory:
             // 2 halo buffers + as many weight stages as fit
-            const int kk = L.expanded ? 1 : L.k, pp = L.expanded ? 0 : L.pad;     // expanded conv0 = 1x1 over the tap-expanded buffer
+            const int kk = L.k, pp = L.pad;
             p.halo = 1; p.ksize = kk; p.pad = pp;
             if (L.sub >= 0) {
                 p.sub = 1; p.sub_py = L.sub >> 1; p.sub_px = L.sub & 1;
@@ -972,17 +906,8 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
             cols = 32;
             while (cols < (persist ? 2 : 1) * p.ns * p.ks * L.cout) cols *= 2;
             p.tmem_cols = cols;
-            if (L.sub >= 0 && !persist) return fail(DSU_E_INVALID, "sub-pixel layers need the persistent halo kernel: " + L.name);
-            if (persist) CUDA_TRY(launch_conv_halo_persist(p, st));
-            else CUDA_TRY(launch_conv_halo(p, st));
-        } else if (L.ric && ric_persist_mode != 0 && L.cout <= (ric_persist_mode == 2 ? 128 : 64)) {
-            // persistent CTAs, epilogue overlapped with the next tile (two accumulator sets in TMEM)
-            p.ks = std::max(1, std::min(p.ks, 256 / L.cout));
-            p.sb = (p.sb / p.ks) * p.ks;
-            cols = 32;
-            while (cols < 2 * p.ks * L.cout) cols *= 2;
-            p.tmem_cols = cols;
-            CUDA_TRY(launch_conv_ric_persist(p, st));
+            if (!persist) return fail(DSU_E_INVALID, "halo convolution: two accumulator sets do not fit in tensor memory: " + L.name);
+            CUDA_TRY(launch_conv_halo_persist(p, st));
         } else {
             bool first = false;
             if (L.first && first_mode != 0) {
@@ -1008,7 +933,7 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
             }
             if (first) CUDA_TRY(launch_conv_first(p, st));
             else {
-                pick_stages(false, p.b_bytes, &p.sa, &p.sb);
+                pick_stages(p.b_bytes, &p.sa, &p.sb);
                 p.ks = 1;
                 CUDA_TRY(launch_conv(p, st));
             }
@@ -1059,11 +984,13 @@ int dsu_create(const dsu_config* cfg, dsu_handle* out) {
     dsu_engine* E = new dsu_engine();
     E->cfg = *cfg;
     E->knobs = knobs_from_env();
-    // stage 1 runs the tensor-memory RIC kernel unless a layer is wider than its TMEM budget allows (then, or with
-    // DSU_RIC_TM=0, the round-1 kernels)
-    E->ric_tm = cfg->kind == DSU_KIND_GENERATORJ_RIC && E->knobs.ric_tm != 0;
+    // stage 1 runs the tensor-memory RIC kernel: accumulator + two A stages must fit the 512 TMEM columns
+    E->ric_tm = cfg->kind == DSU_KIND_GENERATORJ_RIC;
     for (int i = 0; i < 6; ++i)
-        if (cfg->filters[i] > 224) E->ric_tm = false;
+        if (E->ric_tm && cfg->filters[i] > 224) {
+            delete E;
+            return fail(DSU_E_INVALID, "GeneratorJ_RIC: filters must be <= 224 (tensor-memory budget of the RIC kernel)");
+        }
     E->cin_pad = (cfg->input_channels + 7) / 8 * 8;
     E->exact = cfg->precision == DSU_PREC_FP16X3;
     E->f32_acts = E->ric_tm && E->exact;
@@ -1138,9 +1065,8 @@ int dsu_set_knob(dsu_handle h, const char* name, int32_t value) {
     if (!h || !name) return fail(DSU_E_INVALID, "null argument");
     for (const KnobName& kn : kKnobNames)
         if (std::strcmp(kn.name, name) == 0) {
-            if ((kn.field == &Knobs::subpixel || kn.field == &Knobs::ric_tm) && h->knobs.*(kn.field) != value)
-                return fail(DSU_E_STATE, std::string("'") + name + "' shapes the launch plan: set DSU_" + (kn.field == &Knobs::subpixel ? "SUBPIXEL" : "RIC_TM") +
-                                             " in the environment before dsu_create");
+            if (kn.field == &Knobs::subpixel && h->knobs.subpixel != value)
+                return fail(DSU_E_STATE, "'subpixel' shapes the launch plan: set DSU_SUBPIXEL in the environment before dsu_create");
             h->knobs.*(kn.field) = value;
             return DSU_OK;
         }
@@ -1286,7 +1212,7 @@ int dsu_profile_forward(dsu_handle h, int32_t B, int32_t H, int32_t W, int32_t r
 const char* dsu_step_name(dsu_handle h, int32_t index) {
     if (!h || index < 0 || index >= static_cast<int>(h->steps.size())) return "";
     const Step& sp = h->steps[index];
-    return sp.type == 0 ? h->layers[sp.layer].name.c_str() : (sp.type == 1 ? "maxpool" : "ric_expand");
+    return sp.type == 0 ? h->layers[sp.layer].name.c_str() : "maxpool";
 }
 
 int dsu_frames_to_tensor(const uint8_t* color_dev, const uint8_t* pos_dev, const uint8_t* edge_dev,
@@ -1321,7 +1247,7 @@ int dsu_debug_watchdog(dsu_handle h, uint64_t* out, int32_t n) {
     if (!h || !out) return fail(DSU_E_INVALID, "null argument");
     int found = 0;
     for (int i = 0; i < n; ++i) {
-        out[i] = (h->wd_host && i < 32) ? h->wd_host[i] : 0;
+        out[i] = (h->wd_host && i < 32 + 5 * 1024) ? h->wd_host[i] : 0;
         if (out[i]) ++found;
     }
     return found;

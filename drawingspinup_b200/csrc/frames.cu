@@ -216,61 +216,6 @@ __global__ void pos2edge_kernel(const uchar4* __restrict__ pos, int B, int H, in
     edge[p] = best > 0.3 ? 255 : 0;
 }
 
-// Stage-1 conv0 (RIC over the 6(+2)-channel network input): materialise the 9 sampled taps of every pixel
-// once - [pix][tap*cg8 + c] fp16 - so the convolution itself becomes a plain 1x1 contraction over 9*cg8
-// channels.  (Inside the fused RIC kernel a 1-slot block leaves 7/8 of the producer threads idle.)
-// Same arithmetic as ric_producer.cuh: zero outside the image, fp32 blend, static corner set per rotated tap.
-__global__ void ric_expand_kernel(const __half* __restrict__ src_hi, const __half* __restrict__ src_lo, int pitch, int choff,
-                                  int groups, int B, int H, int W, const float2* __restrict__ lyx_tab,
-                                  const uint8_t* __restrict__ oct_tab, __half* dst_hi, __half* dst_lo) {
-    const size_t t = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-    const size_t npf = static_cast<size_t>(H) * W;
-    if (t >= npf * B * groups) return;
-    const int g = static_cast<int>(t % groups);
-    const size_t p = t / groups;
-    const size_t e = p % npf;
-    const int x = static_cast<int>(e % W), y = static_cast<int>(e / W);
-    const size_t frame = (p / npf) * npf;
-    float nf[9][8];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-        const int vy = y + k / 3 - 1, vx = x + k % 3 - 1;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) nf[k][c] = 0.0f;
-        if (static_cast<unsigned>(vy) < static_cast<unsigned>(H) && static_cast<unsigned>(vx) < static_cast<unsigned>(W)) {
-            const size_t off = (frame + static_cast<size_t>(vy) * W + vx) * pitch + choff + g * 8;
-            const uint4 raw = *reinterpret_cast<const uint4*>(src_hi + off);
-            const __half2* h = reinterpret_cast<const __half2*>(&raw);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) { const float2 f = __half22float2(h[c]); nf[k][2 * c] = f.x; nf[k][2 * c + 1] = f.y; }
-            if (src_lo) {
-                const uint4 rl = *reinterpret_cast<const uint4*>(src_lo + off);
-                const __half2* hl = reinterpret_cast<const __half2*>(&rl);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) { const float2 f = __half22float2(hl[c]); nf[k][2 * c] += f.x; nf[k][2 * c + 1] += f.y; }
-            }
-        }
-    }
-    const int oct = oct_tab[e];
-    const int opitch = 9 * groups * 8;
-    __half* oh = dst_hi + p * opitch + g * 8;
-    __half* ol = dst_lo ? dst_lo + p * opitch + g * 8 : nullptr;
-    store8(oh + 4 * groups * 8, ol ? ol + 4 * groups * 8 : nullptr, nf[4]);          // centre tap
-#pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        const float2 l = lyx_tab[e * 8 + m];
-        const float hy = 1.0f - l.x, hx = 1.0f - l.y;
-        const float w00 = hy * hx, w01 = hy * l.y, w10 = l.x * hx, w11 = l.x * l.y;
-        const int r0 = (m >= 2 && m <= 5) ? 0 : 1, c0 = (m >= 4) ? 0 : 1;
-        float o[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-            o[c] = fmaf(w11, nf[(r0 + 1) * 3 + c0 + 1][c], fmaf(w10, nf[(r0 + 1) * 3 + c0][c],
-                   fmaf(w01, nf[r0 * 3 + c0 + 1][c], w00 * nf[r0 * 3 + c0][c])));
-        const int kq = (m - oct) & 7, tap = kq + (kq >> 2);
-        store8(oh + tap * groups * 8, ol ? ol + tap * groups * 8 : nullptr, o);
-    }
-}
 
 inline unsigned blocks_for(size_t n, int threads) { return static_cast<unsigned>((n + threads - 1) / threads); }
 
@@ -306,12 +251,6 @@ cudaError_t maxpool2_f32(const float* in, int in_pitch, int in_choff, int B, int
                          cudaStream_t st) {
     const size_t total = static_cast<size_t>(B) * (Hin / 2) * (Win / 2) * (C / 4);
     maxpool2_f32_kernel<<<blocks_for(total, 256), 256, 0, st>>>(in, in_pitch, in_choff, B, Hin, Win, C, out, out_pitch);
-    return cudaGetLastError();
-}
-cudaError_t ric_expand(const __half* src_hi, const __half* src_lo, int pitch, int choff, int groups, int B, int H, int W,
-                       const float2* lyx, const uint8_t* oct, __half* dst_hi, __half* dst_lo, cudaStream_t st) {
-    const size_t total = static_cast<size_t>(B) * H * W * groups;
-    ric_expand_kernel<<<blocks_for(total, 128), 128, 0, st>>>(src_hi, src_lo, pitch, choff, groups, B, H, W, lyx, oct, dst_hi, dst_lo);
     return cudaGetLastError();
 }
 cudaError_t to_image_space(const float* x, uint8_t* out, size_t n, cudaStream_t st) {

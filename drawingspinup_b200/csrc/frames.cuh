@@ -17,8 +17,6 @@ cudaError_t frames_to_tensor(const uint8_t* color, const uint8_t* pos, const uin
                              float* pre, float* mask, cudaStream_t st);
 cudaError_t maxpool2(const __half* in_hi, const __half* in_lo, int in_pitch, int in_choff, int B, int Hin, int Win, int C,
                      __half* out_hi, __half* out_lo, int out_pitch, cudaStream_t st);
-cudaError_t ric_expand(const __half* src_hi, const __half* src_lo, int pitch, int choff, int groups, int B, int H, int W,
-                       const float2* lyx, const uint8_t* oct, __half* dst_hi, __half* dst_lo, cudaStream_t st);
 cudaError_t to_image_space(const float* x, uint8_t* out, size_t n, cudaStream_t st);
 cudaError_t overlap_edge(const uint8_t* edge, uint8_t* rgba, size_t npix, cudaStream_t st);
 cudaError_t compose_rgba(const float* y, const float* mask, int B, int H, int W, uint8_t* out, cudaStream_t st);

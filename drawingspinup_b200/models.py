@@ -92,7 +92,7 @@ class _Generator(nn.Module):
 
     def __init__(self, norm_layer='batch_norm', gpu_ids=None, use_bias=False, resnet_blocks=9, tanh=False,
                  filters=(64, 128, 128, 128, 128, 64), input_channels=3, append_smoothers=False,
-                 precision: Optional[str] = None):
+                 precision: Optional[str] = None, deterministic: Optional[bool] = None):
         super().__init__()
         assert norm_layer in [None, 'batch_norm', 'instance_norm'], \
             "norm_layer should be None, 'batch_norm' or 'instance_norm', not {}".format(norm_layer)
@@ -107,6 +107,9 @@ class _Generator(nn.Module):
         self.tanh = bool(tanh)
         self.filters = tuple(int(v) for v in filters)
         self.input_channels = int(input_channels)
+        # deterministic=True: bit-reproducible results run to run (stage 1 then issues its MMAs from ONE warp; by default six
+        # warps accumulate into one TMEM accumulator in a timing-dependent order, reproducible to ~1e-7 relative only)
+        self.deterministic = bool(int(os.environ.get("DSU_DETERMINISTIC", "0"))) if deterministic is None else bool(deterministic)
         self.precision = precision or os.environ.get("DSU_PRECISION", "fp16x3")
         if self.precision not in capi.PRECISIONS:
             raise ValueError("precision must be one of %s" % sorted(capi.PRECISIONS))
@@ -189,6 +192,8 @@ class _Generator(nn.Module):
             h = C.c_void_p()
             capi.check(lib.dsu_create(C.byref(cfg), C.byref(h)), "dsu_create")
             self._handle, self._handle_dev = h, idx
+            if self.deterministic:
+                capi.check(lib.dsu_set_knob(h, b"tm_ni", 1), "dsu_set_knob(tm_ni)")
         sig = self._signature()
         if sig != self._loaded_sig:
             for key, t in self.state_dict().items():

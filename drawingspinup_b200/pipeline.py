@@ -72,11 +72,11 @@ class StylizationPipeline:
     """Stage-1 ``GeneratorJ_RIC`` + stage-2 ``GeneratorJ`` of one character on one GPU."""
 
     def __init__(self, sd_stage1, sd_stage2, device, precision: str = "fp16x3", args: Optional[dict] = None,
-                 batch: int = 16):
+                 batch: int = 16, deterministic: bool = False):
         self.device = torch.device(device)
         self.batch = int(batch)
         a = dict(DEFAULT_ARGS if args is None else args)
-        self.g1 = GeneratorJ_RIC(precision=precision, **a)
+        self.g1 = GeneratorJ_RIC(precision=precision, deterministic=deterministic, **a)
         self.g1.load_state_dict(sd_stage1)
         self.g1 = self.g1.to(self.device).eval()
         # sd_stage2 = None: stage 1 only (test_stage1.py alone; BASELINE configs[4]) - run() then returns the stage-1 RGBA

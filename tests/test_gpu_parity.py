@@ -28,13 +28,13 @@ def dev():
     return torch.device("cuda:0")
 
 
-def _model(stage, dev, precision="fp16x3", args=None, seed=1234, **sd_kw):
+def _model(stage, dev, precision="fp16x3", args=None, seed=1234, deterministic=False, **sd_kw):
     a = dict(DEFAULT_ARGS if args is None else args)
     cls = dsu.GeneratorJ_RIC if stage == 1 else dsu.GeneratorJ
     sd = synth.to_torch_state_dict(synth.make_state_dict(
         stage, seed=seed, filters=a["filters"], resnet_blocks=a["resnet_blocks"], input_channels=a["input_channels"],
         tanh=a["tanh"], append_smoothers=a["append_smoothers"], use_bias=a["use_bias"], out_gain=0.25, **sd_kw))
-    m = cls(precision=precision, **a)
+    m = cls(precision=precision, deterministic=deterministic, **a)
     m.load_state_dict(sd)
     return m.to(dev).eval(), sd
 
@@ -197,22 +197,7 @@ def test_reference_on_gpu_agrees_with_cpu_oracle(dev):
         assert (y - ref).abs().max().item() < 2e-5
 
 
-# ------------------------------------------------------------------ the round-1 RIC kernels stay covered (DSU_RIC_TM=0)
-@pytest.mark.parametrize("precision,tol", [("fp16x3", TOL), ("fp16", TOL_FP16)])
-@pytest.mark.parametrize("persist", [2, 0])
-def test_round1_ric_kernels_still_match_oracle(dev, monkeypatch, precision, tol, persist):
-    """Stage 1 normally runs the tensor-memory kernel (conv_ric_tm.cu).  DSU_RIC_TM=0 at create time selects the round-1
-    path - persistent RIC kernel (ric_persist=2) or the non-persistent one (0), tap expansion / fused first layer - which
-    remains the fallback for layers wider than the TMEM budget; both must keep meeting the same bounds."""
-    monkeypatch.setenv("DSU_RIC_TM", "0")
-    m, sd = _model(1, dev, precision=precision)
-    x = _frames_tensor(2, 40, 56, seed=19, stage=1)
-    m.set_knob("ric_persist", persist, device=dev)
-    with torch.no_grad():
-        y = m(x.to(dev)).cpu()
-    assert (y - _oracle(1, sd, x)).abs().max().item() < tol
-
-
+# ------------------------------------------------------------------ tensor-memory RIC kernel configurations
 def test_tensor_memory_kernel_issuer_and_stage_knobs(dev):
     """The tensor-memory RIC kernel with 1 / 3 issuing warps and the minimum weight ring gives the same result as the default
     configuration up to fp32 accumulation order (several warps accumulate into one TMEM accumulator)."""
@@ -232,7 +217,9 @@ def test_tensor_memory_kernel_issuer_and_stage_knobs(dev):
 # ------------------------------------------------------------------ size-independent properties at full size
 @pytest.mark.parametrize("stage", [1, 2])
 def test_batch_invariance_and_determinism_512(dev, stage):
-    m, _ = _model(stage, dev, precision="fp16")
+    """Bit-reproducible in deterministic mode (stage 1: one issuing warp; stage 2 always).  The default stage-1 configuration
+    lets six warps accumulate into one TMEM accumulator, so repeated runs agree to fp32 accumulation order only."""
+    m, _ = _model(stage, dev, precision="fp16", deterministic=True)
     x = _frames_tensor(3, 512, 512, seed=21, stage=stage).to(dev)
     with torch.no_grad():
         full = m(x)
@@ -241,6 +228,15 @@ def test_batch_invariance_and_determinism_512(dev, stage):
     assert torch.equal(full, again)                      # deterministic
     assert torch.equal(full[1:2], one)                   # KAT (vi): a frame does not depend on its batch
     assert torch.isfinite(full).all() and full.abs().max().item() <= 1.0
+    if stage == 1:
+        # default (six issuing warps) vs deterministic, in the parity-grade mode: accumulation-order noise only.  (In the fp16
+        # mode a last-bit fp32 difference can flip an fp16 rounding of an activation, so two orders differ at that mode's own
+        # error level, ~1e-3; both stay within its bound against the oracle.)
+        det, _ = _model(stage, dev, precision="fp16x3", deterministic=True)
+        fast, _ = _model(stage, dev, precision="fp16x3")
+        with torch.no_grad():
+            ref, a, b = det(x), fast(x), fast(x[1:2])
+        assert (a - ref).abs().max().item() < 1e-4 and (a[1:2] - b).abs().max().item() < 1e-4
 
 
 def test_frame_size_528_partial_tiles(dev):
@@ -258,7 +254,7 @@ def test_frame_size_528_partial_tiles(dev):
 
 def test_stage1_dead_smoother_weights_do_not_matter(dev):
     """KAT (iii), models.py:348-352: conv_11_a.0 / .2 are loaded (strict keys) but never influence stage 1."""
-    m, sd = _model(1, dev)
+    m, sd = _model(1, dev, deterministic=True)
     x = _frames_tensor(1, 48, 48, seed=2, stage=1).to(dev)
     with torch.no_grad():
         a = m(x)
@@ -363,7 +359,7 @@ def test_fused_frame_path_equals_unfused_steps(dev):
     b, h, w = 2, 64, 48
     color, pos, edge = synth.make_frames(b, h, w, seed=6)
     for stage in (1, 2):
-        m, sd = _model(stage, dev)
+        m, sd = _model(stage, dev, deterministic=True)
         c, p = torch.from_numpy(color).to(dev), torch.from_numpy(pos).to(dev)
         e = torch.from_numpy(edge).to(dev) if stage == 2 else None
         with torch.no_grad():
@@ -383,7 +379,7 @@ def test_two_stage_chain_against_oracle_chain(dev):
     color, pos, edge = synth.make_frames(b, h, w, seed=13)
     sd1 = synth.to_torch_state_dict(synth.make_state_dict(1, out_gain=0.25))
     sd2 = synth.to_torch_state_dict(synth.make_state_dict(2, out_gain=0.25))
-    pipe = StylizationPipeline(sd1, sd2, dev, precision="fp16x3", batch=2)
+    pipe = StylizationPipeline(sd1, sd2, dev, precision="fp16x3", batch=2, deterministic=True)
     out2, out1 = pipe.run(torch.from_numpy(color).to(dev), torch.from_numpy(pos).to(dev),
                           torch.from_numpy(edge).to(dev), keep_stage1=True)
     out1, out2 = out1.cpu().numpy(), out2.cpu().numpy()
@@ -457,7 +453,7 @@ def test_multi_gpu_shard_equivalence(dev):
     single = None
     for r in range(2):
         d = torch.device("cuda", r)
-        pipe = StylizationPipeline(sd1, sd2, d, precision="fp16", batch=4)
+        pipe = StylizationPipeline(sd1, sd2, d, precision="fp16", batch=4, deterministic=True)
         lo, hi = shard_range(6, r, 2)
         outs.append(pipe.run(*(torch.from_numpy(a[lo:hi]).to(d) for a in (color, pos, edge))).cpu())
         if r == 0:
