@@ -56,11 +56,15 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 }
 
 // 32 channels of one pixel -> fp16 NHWC (hi plane, plus the split-fp16 lo plane when kLo and `lo` is non-null)
-template <bool kLo>
+// kWide = false: 128-bit stores only.  (The tensor-memory RIC kernel runs its epilogue in a non-inlined, register-tight
+// function; there ptxas 12.9 assembled the predicated st.global.v8.b32 of one instantiation as a plain 32-bit STG - only the
+// first word of every 32 bytes reached memory, found as "channels 0,1 of each batch correct, the rest zero".)
+template <bool kLo, bool kWide = true>
 __device__ __forceinline__ void store32(__half* hi, __half* lo, const float* f) {
     // 32-byte aligned destinations (every buffer whose pixel pitch and channel offset are multiples of 16 channels) take
-    // two 256-bit stores; the address test is warp-uniform for such buffers
-    const bool wide = (reinterpret_cast<uintptr_t>(hi) & 31u) == 0;
+    // two 256-bit stores.  The choice is made warp-uniform (a 40-channel pitch aligns only every other pixel): the epilogue's
+    // tcgen05.ld / tcgen05.st are warp-collective and must never be reached by a diverged warp
+    const bool wide = kWide && __all_sync(__activemask(), (reinterpret_cast<uintptr_t>(hi) & 31u) == 0);   // (lanes of pixels outside the image are not here)
     if (kLo && lo) {
         uint4 h[4], l[4];
 #pragma unroll
@@ -86,8 +90,9 @@ __device__ __forceinline__ void store32(__half* hi, __half* lo, const float* f) 
 }
 
 // 32 channels of one pixel -> fp32 NHWC (stage-1 activations of the split-fp16 mode); 32-byte aligned rows take 256-bit stores
+template <bool kWide = true>
 __device__ __forceinline__ void store32_f32(float* dst, const float* f) {
-    if ((reinterpret_cast<uintptr_t>(dst) & 31u) == 0) {
+    if (kWide && __all_sync(__activemask(), (reinterpret_cast<uintptr_t>(dst) & 31u) == 0)) {      // warp-uniform, see store32
 #pragma unroll
         for (int c = 0; c < 4; ++c)
             st_global_256(dst + 8 * c, make_uint4(__float_as_uint(f[8 * c]), __float_as_uint(f[8 * c + 1]), __float_as_uint(f[8 * c + 2]), __float_as_uint(f[8 * c + 3])),
@@ -103,7 +108,7 @@ __device__ __forceinline__ void store32_f32(float* dst, const float* f) {
 // second affine and the lo plane are compile-time (dispatched once per row in epilogue_row): with run-time tests inside
 // the 32-element loops a batch cost ~210 instructions (113 of them branches) on a latency-bound lone warp
 // (profiles/r01m_conv_first.ncu-rep), this form ~70 + the stores.
-template <int kAct, int kScale2, bool kLo>   // kAct / kScale2 = -1: decided at run time (cold generic variant)
+template <int kAct, int kScale2, bool kLo, bool kWide = true>   // kAct / kScale2 = -1: decided at run time (cold generic variant)
 __device__ __forceinline__ void epilogue_batch(const ConvParams& p, const float* s_par, const uint32_t* v, size_t opix, int cb,
                                                bool tail, float* y3) {
     const EpiParams& e = p.epi;
@@ -154,17 +159,17 @@ __device__ __forceinline__ void epilogue_batch(const ConvParams& p, const float*
 #pragma unroll
         for (int c = 0; c < 8; ++c) rp[c] = make_float4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]);
     }
-    if (e.out2_f32) store32_f32(e.out2_f32 + opix * e.out2_pitch + e.out2_choff + cb, f);
+    if (e.out2_f32) store32_f32<kWide>(e.out2_f32 + opix * e.out2_pitch + e.out2_choff + cb, f);
     else if (e.out2_hi)
-        store32<kLo>(e.out2_hi + opix * e.out2_pitch + e.out2_choff + cb,
+        store32<kLo, kWide>(e.out2_hi + opix * e.out2_pitch + e.out2_choff + cb,
                      e.out2_lo ? e.out2_lo + opix * e.out2_pitch + e.out2_choff + cb : nullptr, f);
     if (e.out_relu) {
 #pragma unroll
         for (int c = 0; c < 32; ++c) f[c] = fmaxf(f[c], 0.0f);
     }
-    if (e.out_f32) store32_f32(e.out_f32 + opix * e.out_pitch + e.out_choff + cb, f);
+    if (e.out_f32) store32_f32<kWide>(e.out_f32 + opix * e.out_pitch + e.out_choff + cb, f);
     else if (e.out_hi)
-        store32<kLo>(e.out_hi + opix * e.out_pitch + e.out_choff + cb,
+        store32<kLo, kWide>(e.out_hi + opix * e.out_pitch + e.out_choff + cb,
                      e.out_lo ? e.out_lo + opix * e.out_pitch + e.out_choff + cb : nullptr, f);
     if (tail) {
 #pragma unroll
@@ -183,7 +188,7 @@ __device__ __forceinline__ void epilogue_batch(const ConvParams& p, const float*
 // warp-collective); chalf is warp-uniform.
 // `nsplit` partial accumulators `split_stride` columns apart (K-split issuers) are summed first.
 constexpr uint32_t kEpiAll = 0xFFFFu, kEpiFp16 = 0x0027u, kEpiSplit = 0x2700u;   // variant masks (bit = variant index)
-template <uint32_t kMask = kEpiAll, bool kSub = false>
+template <uint32_t kMask = kEpiAll, bool kSub = false, bool kWide = true>
 __device__ __forceinline__ void epilogue_row(const ConvParams& p, const float* s_par, uint32_t t_addr,
                                              int n, int oy, int ox, int chalf, int nsplit = 1, int split_stride = 0, int csplit = 2) {
     const EpiParams& e = p.epi;
@@ -203,6 +208,7 @@ __device__ __forceinline__ void epilogue_row(const ConvParams& p, const float* s
     for (int cbi = cb_first; cbi < ncb; cbi += cb_step) {
         const int cb = cbi * 32;
         uint32_t v[32];
+        __syncwarp();            // lanes of out-of-image pixels skipped the previous batch: reconverge before the warp-collective load
         tmem_ld32(t_addr + cb, v);
         tmem_ld_wait();
         for (int sp = 1; sp < nsplit; ++sp) {
@@ -217,7 +223,7 @@ __device__ __forceinline__ void epilogue_row(const ConvParams& p, const float* s
         // kMask limits what a kernel instantiates (code size), anything else runs the cold run-time variant
 #define DSU_EPI_CASE(N, A, S2, LO)                                                                                        \
     case N:                                                                                                               \
-        if constexpr ((kMask >> N) & 1u) { epilogue_batch<A, S2, LO>(p, s_par, v, opix, cb, tail, y3); handled = true; } \
+        if constexpr ((kMask >> N) & 1u) { epilogue_batch<A, S2, LO, kWide>(p, s_par, v, opix, cb, tail, y3); handled = true; } \
         break;
         bool handled = false;
         switch (variant) {
@@ -231,7 +237,7 @@ __device__ __forceinline__ void epilogue_row(const ConvParams& p, const float* s
             DSU_EPI_CASE(13, 1, 1, true)
             default: break;
         }
-        if (!handled) epilogue_batch<-1, -1, true>(p, s_par, v, opix, cb, tail, y3);
+        if (!handled) epilogue_batch<-1, -1, true, kWide>(p, s_par, v, opix, cb, tail, y3);
 #undef DSU_EPI_CASE
     }
     if (tail && pix_ok) {

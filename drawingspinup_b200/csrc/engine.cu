@@ -93,6 +93,7 @@ struct Knobs {
     int halo_persist = 2, halo_ns = 0, halo_ks = 0, halo_na = 0, halo_sb = 0, halo_tps = 0;
     int subpixel = 1;         // plan-time: stage-2 nearest-x2 + 3x3 as four 2x2 sub-pixel convolutions
     int tm_ni = 0, tm_sb = 0; // tensor-memory kernel: issuing warps / weight stages (0 = planner decides)
+    int derive_edge = 0;      // stage 2, no edge map passed: burn the edges pos2edge finds in the pos frames (fused into the ingest)
     int tm_trace = 0;         // development: 1 + index of the launch step whose CTA 0 records an event trace (dsu_debug_watchdog slots 32..)
 };
 struct KnobName { const char* name; int Knobs::*field; };
@@ -100,7 +101,7 @@ const KnobName kKnobNames[] = {
     {"first", &Knobs::first}, {"first_ks", &Knobs::first_ks}, {"first_na", &Knobs::first_na},
     {"first_sets", &Knobs::first_sets}, {"halo_persist", &Knobs::halo_persist}, {"halo_ns", &Knobs::halo_ns},
     {"halo_ks", &Knobs::halo_ks}, {"halo_na", &Knobs::halo_na}, {"halo_sb", &Knobs::halo_sb}, {"halo_tps", &Knobs::halo_tps},
-    {"subpixel", &Knobs::subpixel}, {"tm_ni", &Knobs::tm_ni}, {"tm_sb", &Knobs::tm_sb}, {"tm_trace", &Knobs::tm_trace},
+    {"subpixel", &Knobs::subpixel}, {"tm_ni", &Knobs::tm_ni}, {"tm_sb", &Knobs::tm_sb}, {"tm_trace", &Knobs::tm_trace}, {"derive_edge", &Knobs::derive_edge},
 };
 Knobs knobs_from_env() {
     Knobs k;
@@ -1103,7 +1104,7 @@ int dsu_forward_u8(dsu_handle h, const uint8_t* color_dev, const uint8_t* pos_de
     DEVICE_GUARD(h);
     if ((rc = ensure_shape(h, B, H, W))) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    CUDA_TRY(ingest_u8(color_dev, pos_dev, edge_dev, B, H, W, h->buf_hi[SK0], h->buf_lo[SK0],
+    CUDA_TRY(ingest_u8(color_dev, pos_dev, edge_dev, h->knobs.derive_edge, B, H, W, h->buf_hi[SK0], h->buf_lo[SK0],
                        h->f32_acts ? reinterpret_cast<float*>(h->buf_hi[SK0]) : nullptr, h->buf_C[SK0], h->cfg.filters[0], st));
     return run_network(h, B, H, W, y_dev, out_rgba_dev, color_dev + 3, 4, st);
 }

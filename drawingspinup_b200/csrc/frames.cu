@@ -56,20 +56,6 @@ __global__ void ingest_f32_kernel(const float* __restrict__ x, int cin, int cpad
     }
 }
 
-__global__ void ingest_u8_kernel(const uchar4* __restrict__ color, const uchar4* __restrict__ pos,
-                                 const uint8_t* __restrict__ edge, size_t npix,
-                                 __half* hi, __half* lo, float* f32, int pitch, int choff) {
-    const size_t p = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-    if (p >= npix) return;
-    uchar4 c = color[p];
-    const uchar4 q = pos[p];
-    const float mask = __fdiv_rn(static_cast<float>(c.w), 255.0f);      // alpha BEFORE the edge burn-in (data.py:28)
-    if (edge && edge[p] < 255) { c.x = 0; c.y = 0; c.z = 0; }           // overlap_edge_on_img
-    float v[8] = {norm_u8(c.x), norm_u8(c.y), norm_u8(c.z), mask, norm_u8(q.x), norm_u8(q.y), 0.0f, 0.0f};
-    if (f32) store8_f32(f32 + p * pitch + choff, v);
-    else store8(hi + p * pitch + choff, lo ? lo + p * pitch + choff : nullptr, v);
-}
-
 __global__ void frames_to_tensor_kernel(const uchar4* __restrict__ color, const uchar4* __restrict__ pos,
                                         const uint8_t* __restrict__ edge, size_t npix_frame, size_t npix,
                                         float* __restrict__ pre, float* __restrict__ mask_out) {
@@ -183,13 +169,7 @@ __global__ void compose_rgba_kernel(const float* __restrict__ y, const float* __
 
 // pos2edge (run_render.py:31-57): per channel Sobel-3 (BORDER_REFLECT_101) in float64 on u8/255 with
 // the background (alpha < 255) forced to 2, max magnitude over the 3 channels > 0.3.
-__global__ void pos2edge_kernel(const uchar4* __restrict__ pos, int B, int H, int W, uint8_t* __restrict__ edge) {
-    const size_t p = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-    const size_t npf = static_cast<size_t>(H) * W;
-    if (p >= npf * B) return;
-    const int x = static_cast<int>(p % W);
-    const int y = static_cast<int>((p / W) % H);
-    const uchar4* f = pos + (p / npf) * npf;
+__device__ __forceinline__ bool pos_is_edge(const uchar4* __restrict__ f, int x, int y, int H, int W) {
     double v[3][3][3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -213,7 +193,36 @@ __global__ void pos2edge_kernel(const uchar4* __restrict__ pos, int B, int H, in
         const double gy = (v[c][2][0] - v[c][0][0]) + 2.0 * (v[c][2][1] - v[c][0][1]) + (v[c][2][2] - v[c][0][2]);
         best = fmax(best, sqrt(gx * gx + gy * gy));
     }
-    edge[p] = best > 0.3 ? 255 : 0;
+    return best > 0.3;
+}
+__global__ void pos2edge_kernel(const uchar4* __restrict__ pos, int B, int H, int W, uint8_t* __restrict__ edge) {
+    const size_t p = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    const size_t npf = static_cast<size_t>(H) * W;
+    if (p >= npf * B) return;
+    edge[p] = pos_is_edge(pos + (p / npf) * npf, static_cast<int>(p % W), static_cast<int>((p / W) % H), H, W) ? 255 : 0;
+}
+
+
+__global__ void ingest_u8_kernel(const uchar4* __restrict__ color, const uchar4* __restrict__ pos,
+                                 const uint8_t* __restrict__ edge, int derive_edge, int H, int W, size_t npix,
+                                 __half* hi, __half* lo, float* f32, int pitch, int choff) {
+    const size_t p = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (p >= npix) return;
+    uchar4 c = color[p];
+    const uchar4 q = pos[p];
+    const float mask = __fdiv_rn(static_cast<float>(c.w), 255.0f);      // alpha BEFORE the edge burn-in (data.py:28)
+    // overlap_edge_on_img: burn where the stored edge map (255 - pos2edge, run_render.py:117-120) is < 255.  derive_edge: no edge
+    // map given - the same predicate straight from the pos frame (pos2edge fused into the ingest, nothing crosses PCIe)
+    bool burn = false;
+    if (edge) burn = edge[p] < 255;
+    else if (derive_edge) {
+        const size_t npf = static_cast<size_t>(H) * W;
+        burn = pos_is_edge(pos + (p / npf) * npf, static_cast<int>(p % W), static_cast<int>((p / W) % H), H, W);
+    }
+    if (burn) { c.x = 0; c.y = 0; c.z = 0; }
+    float v[8] = {norm_u8(c.x), norm_u8(c.y), norm_u8(c.z), mask, norm_u8(q.x), norm_u8(q.y), 0.0f, 0.0f};
+    if (f32) store8_f32(f32 + p * pitch + choff, v);
+    else store8(hi + p * pitch + choff, lo ? lo + p * pitch + choff : nullptr, v);
 }
 
 
@@ -227,11 +236,11 @@ cudaError_t ingest_f32(const float* x, int B, int cin, int cpad, int H, int W, _
     ingest_f32_kernel<<<blocks_for(np, 256), 256, 0, st>>>(x, cin, cpad, npf, np, hi, lo, f32, pitch, choff);
     return cudaGetLastError();
 }
-cudaError_t ingest_u8(const uint8_t* color, const uint8_t* pos, const uint8_t* edge, int B, int H, int W,
+cudaError_t ingest_u8(const uint8_t* color, const uint8_t* pos, const uint8_t* edge, int derive_edge, int B, int H, int W,
                       __half* hi, __half* lo, float* f32, int pitch, int choff, cudaStream_t st) {
     const size_t np = static_cast<size_t>(H) * W * B;
-    ingest_u8_kernel<<<blocks_for(np, 256), 256, 0, st>>>(reinterpret_cast<const uchar4*>(color),
-                                                          reinterpret_cast<const uchar4*>(pos), edge, np, hi, lo, f32, pitch, choff);
+    ingest_u8_kernel<<<blocks_for(np, 256), 256, 0, st>>>(reinterpret_cast<const uchar4*>(color), reinterpret_cast<const uchar4*>(pos), edge,
+                                                          derive_edge, H, W, np, hi, lo, f32, pitch, choff);
     return cudaGetLastError();
 }
 cudaError_t frames_to_tensor(const uint8_t* color, const uint8_t* pos, const uint8_t* edge, int B, int H, int W,

@@ -9,7 +9,8 @@ namespace dsu {
 // `f32` non-null: write fp32 NHWC instead of the fp16 hi[/lo] planes (stage 1 of the split-fp16 mode)
 cudaError_t ingest_f32(const float* x, int B, int cin, int cpad, int H, int W, __half* hi, __half* lo, float* f32, int pitch,
                        int choff, cudaStream_t st);
-cudaError_t ingest_u8(const uint8_t* color, const uint8_t* pos, const uint8_t* edge, int B, int H, int W,
+// edge == nullptr && derive_edge: burn the edges pos2edge would find in `pos` (run_render.py:31-57 fused into the ingest)
+cudaError_t ingest_u8(const uint8_t* color, const uint8_t* pos, const uint8_t* edge, int derive_edge, int B, int H, int W,
                       __half* hi, __half* lo, float* f32, int pitch, int choff, cudaStream_t st);
 cudaError_t maxpool2_f32(const float* in, int in_pitch, int in_choff, int B, int Hin, int Win, int C, float* out, int out_pitch,
                          cudaStream_t st);

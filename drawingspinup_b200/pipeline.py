@@ -72,7 +72,7 @@ class StylizationPipeline:
     """Stage-1 ``GeneratorJ_RIC`` + stage-2 ``GeneratorJ`` of one character on one GPU."""
 
     def __init__(self, sd_stage1, sd_stage2, device, precision: str = "fp16x3", args: Optional[dict] = None,
-                 batch: int = 16, deterministic: bool = False):
+                 batch: int = 16, deterministic: bool = False, derive_edge: bool = False):
         self.device = torch.device(device)
         self.batch = int(batch)
         a = dict(DEFAULT_ARGS if args is None else args)
@@ -85,6 +85,10 @@ class StylizationPipeline:
             self.g2 = GeneratorJ(precision=precision, **a)
             self.g2.load_state_dict(sd_stage2)
             self.g2 = self.g2.to(self.device).eval()
+            if derive_edge:
+                # no edge/NNNN.png needed: stage 2's ingest finds the edges in the pos frames itself (run_render.py:31-57, pos2edge,
+                # fused into the frame-pack kernel); run() / run_host() are then called with edge=None
+                self.g2.set_knob("derive_edge", 1, device=self.device)
 
     @torch.no_grad()
     def run(self, color: torch.Tensor, pos: torch.Tensor, edge: torch.Tensor, keep_stage1: bool = False):
@@ -96,7 +100,8 @@ class StylizationPipeline:
         for lo in range(0, n, self.batch):
             hi = min(n, lo + self.batch)
             r1 = self.g1.forward_frames(color[lo:hi], pos[lo:hi], None)
-            out[lo:hi] = self.g2.forward_frames(r1, pos[lo:hi], edge[lo:hi]) if self.g2 is not None else r1
+            out[lo:hi] = (self.g2.forward_frames(r1, pos[lo:hi], edge[lo:hi] if edge is not None else None)
+                          if self.g2 is not None else r1)
             if mid is not None:
                 mid[lo:hi] = r1
         return (out, mid) if keep_stage1 else out
@@ -124,7 +129,7 @@ class StylizationPipeline:
         def upload(span):
             lo, hi = span
             with torch.cuda.stream(cs):
-                bufs = tuple(t[lo:hi].to(self.device, non_blocking=True) for t in (color, pos, edge))
+                bufs = tuple(t[lo:hi].to(self.device, non_blocking=True) if t is not None else None for t in (color, pos, edge))
                 ev = torch.cuda.Event()
                 ev.record(cs)
             return bufs, ev
@@ -146,7 +151,8 @@ class StylizationPipeline:
                 if mid is not None:
                     mid[lo:hi].copy_(r1, non_blocking=True)
             for t in (c, p, e):
-                t.record_stream(main)          # allocated on the copy stream, consumed by the kernels
+                if t is not None:
+                    t.record_stream(main)      # allocated on the copy stream, consumed by the kernels
             r2.record_stream(cs)               # produced on the main stream, downloaded on the copy stream
             if mid is not None:
                 r1.record_stream(cs)

@@ -404,6 +404,22 @@ def test_two_stage_chain_against_oracle_chain(dev):
     assert np.array_equal(host_out.numpy(), out2)
 
 
+def test_pipeline_derives_edges_from_pos(dev):
+    """f1 (run_render.py:31-57, 117-120): with derive_edge the stage-2 ingest burns the edges it finds in the pos frames itself;
+    the result equals the pipeline fed with the edge map the reference would have written (255 - pos2edge), bit for bit."""
+    from drawingspinup_b200.pipeline import StylizationPipeline
+    b, h, w = 2, 64, 80
+    color, pos, _ = synth.make_frames(b, h, w, seed=29)
+    edge = np.stack([255 - rp.pos2edge(pos[i]) for i in range(b)]).astype(np.uint8)
+    assert (edge < 255).any()
+    sd1 = synth.to_torch_state_dict(synth.make_state_dict(1, out_gain=0.25))
+    sd2 = synth.to_torch_state_dict(synth.make_state_dict(2, out_gain=0.25))
+    c_d, p_d, e_d = (torch.from_numpy(a).to(dev) for a in (color, pos, edge))
+    given = StylizationPipeline(sd1, sd2, dev, precision="fp16x3", batch=2, deterministic=True).run(c_d, p_d, e_d)
+    derived = StylizationPipeline(sd1, sd2, dev, precision="fp16x3", batch=2, deterministic=True, derive_edge=True).run(c_d, p_d, None)
+    assert torch.equal(given, derived)
+
+
 def test_c_abi_host_entry_point(dev):
     b, h, w = 1, 32, 48
     color, pos, edge = synth.make_frames(b, h, w, seed=17)

@@ -27,6 +27,8 @@ BUF = dict(SK0=0, P0=1, O1=2, P1=3, O2=4, T=5, U=6, V2=7, V1=8, C11=9, S0=10)
 
 
 def nhwc(m, buf, b, h, w, c, exact):
+    if exact and isinstance(m, dsu.GeneratorJ_RIC):      # stage 1 keeps fp32 activations in split-fp16 mode
+        return m.debug_buffer(BUF[buf], 0, (b, h, w, c), torch.float32).permute(0, 3, 1, 2)
     t = m.debug_buffer(BUF[buf], 0, (b, h, w, c)).float()
     if exact:
         t = t + m.debug_buffer(BUF[buf], 1, (b, h, w, c)).float()
@@ -37,7 +39,10 @@ def main():
     dev = torch.device("cuda:0")
     print("device:", torch.cuda.get_device_name(0), "| frames", (B, H, W))
     color, pos, edge = synth.make_frames(B, H, W, seed=7)
-    for stage, cls in ((2, dsu.GeneratorJ), (1, dsu.GeneratorJ_RIC)):
+    stages = ((2, dsu.GeneratorJ), (1, dsu.GeneratorJ_RIC))
+    if os.environ.get("CHECK_STAGE"):
+        stages = tuple(s for s in stages if s[0] == int(os.environ["CHECK_STAGE"]))
+    for stage, cls in stages:
         sd = synth.to_torch_state_dict(synth.make_state_dict(stage, seed=1234, out_gain=0.25))
         x = torch.from_numpy(np.stack([rp.frame_to_tensor(color[i], pos[i], edge[i] if stage == 2 else None)[0]
                                        for i in range(B)]))

@@ -14,18 +14,10 @@
 
 using namespace dsu;
 
-__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     __half2 h = __floats2half2_rn(lo, hi);
@@ -185,6 +177,170 @@ __global__ void rate_kernel(int n, int issuers, int group, int shared_acc, int s
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// ------------------------------------------------------------------------------------------------ part 5: MMAs under producer traffic
+// 6 issuing warps (warps 0-5) run TS MMAs exactly like part 4 (shared accumulator, `group` MMAs per commit) while 12 other
+// warps (6-17) keep doing what the RIC producers do: 9 x ld.shared.v4 + 9 x tcgen05.st.x4 per item into OTHER columns
+// (bg & 1) and / or packed-half math (bg & 2).  Does the producers' traffic slow the tensor pipe down?
+__global__ void rate_bg_kernel(int n, int group, int bg, int iters, long long* out_cycles) {
+    extern __shared__ uint8_t raw[];
+    const uint32_t raw_u = smem_u32(raw);
+    const uint32_t base = (raw_u + 1023u) & ~1023u;
+    uint8_t* smem = raw + (base - raw_u);
+    const uint32_t b_tile = static_cast<uint32_t>(n) * 32;
+    const uint32_t halo_off = 36 * b_tile;                               // 24 KB "halo tile" for the background loads
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + halo_off + 24576);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 16);
+    volatile int* stop = reinterpret_cast<volatile int*>(slot + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (uint32_t i = tid; i < (halo_off + 24576) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (tid == 0) *stop = 0;
+    fence_proxy_async_smem();
+    if (warp == 0) {
+        if (tid == 0) {
+            for (int i = 0; i < 6; ++i) mbar_init(smem_u32(bar + i), 1);
+            for (int i = 6; i < 14; ++i) mbar_init(smem_u32(bar + i), 1000000);
+            mbar_init(smem_u32(bar + 14), 6 * 32);
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc(smem_u32(slot), 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *slot;
+    const uint32_t a_col = 512 - 72;
+    if (warp < 6) {
+        const uint32_t idesc = umma_idesc_f16(128, n);
+        __syncwarp();
+        const long long t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+            if (elect_one()) {
+                for (int g = 0; g < group; ++g) {
+                    const int q = (it * group + g) % 36;
+                    umma_f16_ts(tmem, tmem + a_col + 8 * (q % 9), umma_desc_noswizzle(base + q * b_tile, 128, 256), idesc, 1u);
+                }
+                umma_commit(smem_u32(bar + 6 + (it & 7)));
+                if (it == iters - 1) umma_commit(smem_u32(bar + warp));
+            }
+            __syncwarp();
+        }
+        mbar_wait(smem_u32(bar + warp), 0);
+        const long long t1 = clock64();
+        if (lane == 0 && blockIdx.x == 0) out_cycles[warp] = t1 - t0;
+        mbar_arrive(smem_u32(bar + 14));
+        if (warp == 0) { mbar_wait(smem_u32(bar + 14), 0); if (lane == 0) *stop = 1; }
+    } else if (bg) {
+        const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+        const uint32_t hb = base + halo_off + ((warp - 6) * 32 + lane) % 160 * 128;
+        uint32_t acc = lane;
+        long long n_items = 0;
+        while (!*stop) {
+            uint32_t v[9][4];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                if (bg & 1) {
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[k][0]), "=r"(v[k][1]), "=r"(v[k][2]), "=r"(v[k][3]) : "r"(hb + ((k * 144) % 2048)));
+                } else { v[k][0] = acc + k; v[k][1] = acc; v[k][2] = k; v[k][3] = acc ^ k; }
+            }
+            if (bg & 2) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+#pragma unroll
+                    for (int k = 0; k < 9; ++k)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            __half2 x = *reinterpret_cast<__half2*>(&v[k][c]);
+                            x = __hfma2(x, x, x);
+                            v[k][c] = *reinterpret_cast<uint32_t*>(&x);
+                        }
+            }
+            if (bg & 1) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k)
+                    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tmem + lane_base + 256 + k * 8), "r"(v[k][0]), "r"(v[k][1]), "r"(v[k][2]), "r"(v[k][3]) : "memory");
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            }
+            acc += v[0][0];
+            ++n_items;
+        }
+        if (lane == 0 && blockIdx.x == 0 && warp == 6) out_cycles[6] = n_items + (acc & 1);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------ part 6: tcgen05.st cost
+// `nw` warps store `per_wait` x (32 lanes x W columns) and then tcgen05.wait::st, in a loop for a fixed number of iterations;
+// optionally 6 other warps keep the tensor pipe saturated with TS MMAs (N = 128).  cycles per store instruction per warp.
+template <int W>
+__device__ __forceinline__ void st_w(uint32_t taddr, uint32_t v) {
+    if constexpr (W == 2) asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %1};" ::"r"(taddr), "r"(v) : "memory");
+    if constexpr (W == 4) asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %1, %1, %1};" ::"r"(taddr), "r"(v) : "memory");
+    if constexpr (W == 8) asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(v) : "memory");
+    if constexpr (W == 16) asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(v) : "memory");
+    if constexpr (W == 32) asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(v) : "memory");
+}
+template <int W>
+__global__ void st_cost_kernel(int nw, int per_wait, int with_mma, int iters, long long* out_cycles) {
+    extern __shared__ uint8_t raw[];
+    const uint32_t raw_u = smem_u32(raw);
+    const uint32_t base = (raw_u + 1023u) & ~1023u;
+    uint8_t* smem = raw + (base - raw_u);
+    const uint32_t b_tile = 128 * 32;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 36 * b_tile);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 16);
+    volatile int* stop = reinterpret_cast<volatile int*>(slot + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (uint32_t i = tid; i < 36 * b_tile / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (tid == 0) *stop = 0;
+    fence_proxy_async_smem();
+    if (warp == 0) {
+        if (tid == 0) { for (int i = 0; i < 8; ++i) mbar_init(smem_u32(bar + i), 1000000); mbar_init(smem_u32(bar + 8), nw * 32); fence_mbar_init(); }
+        __syncwarp();
+        tmem_alloc(smem_u32(slot), 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *slot;
+    if (warp < 6) {
+        if (with_mma) {
+            const uint32_t idesc = umma_idesc_f16(128, 128);
+            int it = 0;
+            while (!*stop) {
+                if (elect_one()) {
+                    for (int g = 0; g < 9; ++g) {
+                        const int q = (it * 9 + g) % 36;
+                        umma_f16_ts(tmem, tmem + 440 + 8 * (q % 9), umma_desc_noswizzle(base + q * b_tile, 128, 256), idesc, 1u);
+                    }
+                    umma_commit(smem_u32(bar + (it & 7)));
+                }
+                __syncwarp();
+                ++it;
+            }
+        }
+    } else if (warp < 6 + nw) {
+        const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+        __syncwarp();
+        const long long t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+            for (int k = 0; k < per_wait; ++k) st_w<W>(tmem + lane_base + 128 + ((k * W) % 256), static_cast<uint32_t>(it + k));
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        const long long t1 = clock64();
+        if (lane == 0 && blockIdx.x == 0 && warp == 6) out_cycles[0] = t1 - t0;
+        mbar_arrive(smem_u32(bar + 8));
+        if (warp == 6) { mbar_wait(smem_u32(bar + 8), 0); if (lane == 0) *stop = 1; }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 int main() {
     float* d_out;
     cudaMalloc(&d_out, 128 * 64 * 4);
@@ -270,5 +426,51 @@ int main() {
                                128.0 * n * 16 / 4096.0, tf);
                     }
     printf("* assuming 1.9 GHz\n");
+    // ---- 5: six issuers under producer-like background traffic of 12 warps
+    cudaFuncSetAttribute(rate_bg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    long long* d_c2;
+    cudaMalloc(&d_c2, 8 * 8);
+    printf("%4s %6s %28s | %12s %8s | %s\n", "N", "group", "background (12 warps)", "cyc/MMA/CTA", "ideal", "bg items per warp");
+    for (int n : {64, 128})
+        for (int group : {3, 9})
+            for (int bg : {0, 1, 2, 3}) {
+                const size_t sm = 36 * n * 32 + 24576 + 256 + 1024;
+                cudaMemset(d_c2, 0, 64);
+                rate_bg_kernel<<<sms, 18 * 32, sm>>>(n, group, bg, 600, d_c2);
+                cudaError_t e = cudaDeviceSynchronize();
+                if (e != cudaSuccess) { printf("rate_bg: CUDA error %s\n", cudaGetErrorString(e)); return 1; }
+                long long cyc[8] = {0};
+                cudaMemcpy(cyc, d_c2, 64, cudaMemcpyDeviceToHost);
+                long long mx = 0;
+                for (int i = 0; i < 6; ++i) mx = cyc[i] > mx ? cyc[i] : mx;
+                const double per = static_cast<double>(mx) / (600.0 * group * 6);
+                printf("%4d %6d %28s | %12.1f %8.1f | %lld\n", n, group,
+                       bg == 0 ? "none" : (bg == 1 ? "ld.shared + tcgen05.st" : (bg == 2 ? "HFMA2 only" : "ld.shared + HFMA2 + tcgen05.st")), per,
+                       128.0 * n * 16 / 4096.0, cyc[6]);
+            }
+    // ---- 6: cost of tcgen05.st by width, with / without a saturated tensor pipe
+    printf("%6s %6s %9s %9s | %14s %14s\n", "width", "warps", "per_wait", "MMAs", "cyc/st/warp", "B/clk/SM");
+    auto st_run = [&](auto kern, int W, int nw, int per_wait, int with_mma) {
+        const size_t sm = 36 * 128 * 32 + 256 + 1024;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaMemset(d_c2, 0, 64);
+        const int iters = 2000;
+        kern<<<sms, 18 * 32, sm>>>(nw, per_wait, with_mma, iters, d_c2);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("st_cost: CUDA error %s\n", cudaGetErrorString(e)); exit(1); }
+        long long cyc = 0;
+        cudaMemcpy(&cyc, d_c2, 8, cudaMemcpyDeviceToHost);
+        const double per = static_cast<double>(cyc) / (static_cast<double>(iters) * per_wait);
+        printf("%6d %6d %9d %9s | %14.1f %14.1f\n", W, nw, per_wait, with_mma ? "N=128" : "none", per, nw * 32.0 * W * 4 / per);
+    };
+    for (int with_mma : {0, 1})
+        for (int nw : {4, 12})
+            for (int per_wait : {1, 9}) {
+                st_run(st_cost_kernel<2>, 2, nw, per_wait, with_mma);
+                st_run(st_cost_kernel<4>, 4, nw, per_wait, with_mma);
+                st_run(st_cost_kernel<8>, 8, nw, per_wait, with_mma);
+                st_run(st_cost_kernel<16>, 16, nw, per_wait, with_mma);
+                st_run(st_cost_kernel<32>, 32, nw, per_wait, with_mma);
+            }
     return 0;
 }
