@@ -119,8 +119,8 @@ constexpr int kTmMaxBlocks = 12;
 constexpr int kTmMaxMaps = 3;
 constexpr int kTmStageCols = 144;        // 9 taps x 2 parts x 8 columns (fp16: two K16 steps; split-fp16: hi and lo of one K16 step)
 constexpr int kTmHaloBytes = 23552;      // 18 x 10 pixel lines of 128 B, rounded up to the 1024-byte swizzle atom
-constexpr int kTmProducerWarps = 12, kTmIssuerWarps = 6, kTmLoaderWarps = 2;      // producers double as the epilogue
-constexpr int kTmThreads = (kTmProducerWarps + kTmIssuerWarps + kTmLoaderWarps) * 32;
+constexpr int kTmProducerWarps = 8, kTmEpilogueWarps = 4, kTmIssuerWarps = 6, kTmLoaderWarps = 2;
+constexpr int kTmThreads = (kTmProducerWarps + kTmEpilogueWarps + kTmIssuerWarps + kTmLoaderWarps) * 32;
 struct TmBlock {
     uint8_t map;            // tensor map (channel run) index
     uint8_t nstages;        // stages of this block that carry weights (1 or 2)

@@ -17,18 +17,8 @@
 // address (impossible with the warp-uniform column of tcgen05.st) to the CODE: eight blend variants selected by the pixel's
 // octant, writing raster-ordered taps; a warp whose pixels straddle an octant boundary runs two variants.
 //
-// Roles (20 warps): 0-11 producers AND epilogue (three per TMEM lane quadrant; the (stage, chunk) items of a quadrant are
-// dealt round-robin to its three warps - item 4 * stage + chunk goes to warp (4 * stage + chunk) % 3 - and the same warps
-// drain / zero the accumulator, column batch b going to warp b % 3), 12-17 MMA issuers, 18 halo loader (TMA tensor loads),
-// 19 weight loader (bulk copies).
-// History (profiles/r02f_trace_*.log, r02j_*): 8 producer warps (two chunks each) + 4 dedicated epilogue warps were latency
-// bound at two warps per scheduler (2.3-2.6 kclk per stage against 1.2-1.7 kclk of MMAs) and, with a single accumulator set
-// for Cout = 128, the lone epilogue warp per quadrant kept the tensor pipe idle for 6-9 kclk per tile; 16 producer warps
-// fit only with 96 registers each and spilled their per-stage state to local memory, which at 200 KB of shared memory
-// per CTA lives in L2 - twice slower.  12 warps at 128 registers do not spill; the epilogue of tile i runs on them after
-// they have produced the first two stages of tile i+1, while the last MMAs of tile i drain.
-#include <type_traits>
-
+// Roles (20 warps): 0-7 producers (two per TMEM lane quadrant: chunk pairs g = 0 / 1 of a stage), 8-11 epilogue,
+// 12-17 MMA issuers, 18 halo loader (TMA tensor loads), 19 weight loader (bulk copies).
 #include "conv_device.cuh"
 
 namespace dsu {
@@ -39,15 +29,14 @@ constexpr int kTmMaxB = 8;                       // weight stages in shared memo
 constexpr int kTmBars = 2 + 2 + 3 + kTmMaxB + kTmMaxB + 2 + 2;
 
 struct TmSmem {
-    uint32_t halo0, b0, par, pcopy, bars, total;
+    uint32_t halo0, b0, par, bars, total;
 };
 __host__ __device__ inline TmSmem tm_smem(int sb, int b_stage_bytes, int cout) {
     TmSmem L;
     L.halo0 = 0;
     L.b0 = 2 * kTmHaloBytes;
     L.par = L.b0 + sb * b_stage_bytes;
-    L.pcopy = (L.par + (7 * cout + 4) * 4 + 15u) & ~15u;          // ConvParams copy for the (non-inlined) epilogue
-    L.bars = (L.pcopy + static_cast<uint32_t>(sizeof(ConvParams)) + 15u) & ~15u;
+    L.bars = (L.par + (7 * cout + 4) * 4 + 15u) & ~15u;
     L.total = L.bars + (kTmBars + 1) * 8;
     return L;
 }
@@ -76,29 +65,25 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
 }
 template <int kSleepNs>
 __device__ __forceinline__ void mbar_wait_wd(uint32_t bar, uint32_t parity, unsigned long long* dbg, uint32_t tag, int a, int b) {
-    if (!mbar_test(bar, parity)) {
-        long long t0 = 0;
-        uint32_t iter = 0;
-        bool reported = false;
-        while (true) {
-            if constexpr (kSleepNs > 0) {
-                asm volatile("nanosleep.u32 %0;" ::"n"(kSleepNs));
-                if (mbar_test(bar, parity)) break;
-            } else {
-                if (mbar_try_wait(bar, parity)) break;
-            }
-            if ((++iter & 0x3FFu) == 0) {                 // the clock is only read every 1024 polls
-                const long long now = clock64();
-                if (t0 == 0) t0 = now;
-                const long long dt = now - t0;
-                if (!reported && dt > 2000000000LL) { tm_watchdog_fire(dbg, tag, a, b); reported = true; }
-                if (dt > 2800000000LL) __trap();
-            }
+    if (mbar_test(bar, parity)) return;
+    long long t0 = 0;
+    uint32_t iter = 0;
+    bool reported = false;
+    while (true) {
+        if constexpr (kSleepNs > 0) {
+            asm volatile("nanosleep.u32 %0;" ::"n"(kSleepNs));
+            if (mbar_test(bar, parity)) return;
+        } else {
+            if (mbar_try_wait(bar, parity)) return;
+        }
+        if ((++iter & 0x3FFu) == 0) {                 // the clock is only read every 1024 polls
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            const long long dt = now - t0;
+            if (!reported && dt > 2000000000LL) { tm_watchdog_fire(dbg, tag, a, b); reported = true; }
+            if (dt > 2800000000LL) __trap();
         }
     }
-    // lanes leave the polling loop at different times: reconverge - what follows a wait in this kernel is warp-collective
-    // (tcgen05.ld / tcgen05.st / elect) and, in one place, a call of a non-inlined function
-    __syncwarp();
 }
 
 template <int kRegs>
@@ -136,31 +121,34 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 __device__ __forceinline__ constexpr int tm_r0(int m) { return (m >= 2 && m <= 5) ? 0 : 1; }
 __device__ __forceinline__ constexpr int tm_c0(int m) { return (m >= 4) ? 0 : 1; }
 
-// ---- one rotated tap m of one pixel from its 2x2 corner set.
-// fp16 mode: 8 channels, packed half2 blend in the operation order of round 1 (w00*n00, then fma w01*n01, w10*n10, w11*n11);
-// W.q = the pixel's 8 x {w00,w01 | w10,w11} fp16 table entry in rotated tap order.
-struct WtsH { uint4 q[4]; };
-struct WtsF { float w[8][4]; };          // split-fp16 mode: fp32 weights (1-ly)(1-lx), (1-ly)lx, ly(1-lx), ly*lx per rotated tap
-struct Lines { uint32_t l[9]; };         // 3x3 neighbour lines of the halo tile, swizzle key in bits 4-6
-
-template <int M>
-__device__ __forceinline__ uint4 blend_tap(const uint4& n00, const uint4& n01, const uint4& n10, const uint4& n11, const WtsH& W) {
-    const uint32_t a = (M & 1) ? W.q[M >> 1].z : W.q[M >> 1].x, b = (M & 1) ? W.q[M >> 1].w : W.q[M >> 1].y;
-    const __half2 wa = *reinterpret_cast<const __half2*>(&a), wb = *reinterpret_cast<const __half2*>(&b);
-    const __half2 w00 = __low2half2(wa), w01 = __high2half2(wa), w10 = __low2half2(wb), w11 = __high2half2(wb);
-    const __half2* p00 = reinterpret_cast<const __half2*>(&n00);
-    const __half2* p01 = reinterpret_cast<const __half2*>(&n01);
-    const __half2* p10 = reinterpret_cast<const __half2*>(&n10);
-    const __half2* p11 = reinterpret_cast<const __half2*>(&n11);
-    uint4 out;
-    __half2* o = reinterpret_cast<__half2*>(&out);
+// ---- fp16 mode: 8 channels of one pixel, packed half2 blend (same operation order as round 1's ric_produce<false, true>:
+// w00*n00, then fma w01*n01, w10*n10, w11*n11), raster-ordered output.  wq = the pixel's 8 x {w00,w01 | w10,w11} fp16 table
+// entry in rotated tap order; octant O maps raster tap t (circle index kq) to rotated tap m = (kq + O) & 7.
+template <int O>
+__device__ __forceinline__ void blend_h(const uint4 (&nb)[9], const uint4 (&wq)[4], uint4 (&out)[9]) {
+    out[4] = nb[4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
-        o[c] = __hfma2(w11, p11[c], __hfma2(w10, p10[c], __hfma2(w01, p01[c], __hmul2(w00, p00[c]))));
-    return out;
+    for (int t = 0; t < 9; ++t) {
+        if (t == 4) continue;
+        const int kq = t < 4 ? t : t - 1;
+        const int m = (kq + O) & 7;
+        const uint32_t a = (m & 1) ? wq[m >> 1].z : wq[m >> 1].x, b = (m & 1) ? wq[m >> 1].w : wq[m >> 1].y;
+        const __half2 wa = *reinterpret_cast<const __half2*>(&a), wb = *reinterpret_cast<const __half2*>(&b);
+        const __half2 w00 = __low2half2(wa), w01 = __high2half2(wa), w10 = __low2half2(wb), w11 = __high2half2(wb);
+        const int r0 = tm_r0(m), c0 = tm_c0(m);
+        const __half2* n00 = reinterpret_cast<const __half2*>(&nb[r0 * 3 + c0]);
+        const __half2* n01 = reinterpret_cast<const __half2*>(&nb[r0 * 3 + c0 + 1]);
+        const __half2* n10 = reinterpret_cast<const __half2*>(&nb[(r0 + 1) * 3 + c0]);
+        const __half2* n11 = reinterpret_cast<const __half2*>(&nb[(r0 + 1) * 3 + c0 + 1]);
+        __half2* o = reinterpret_cast<__half2*>(&out[t]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            o[c] = __hfma2(w11, n11[c], __hfma2(w10, n10[c], __hfma2(w01, n01[c], __hmul2(w00, n00[c]))));
+    }
 }
 
-// split-fp16 mode: 4 fp32 channels, fp32 blend, then split into fp16 hi and lo = fp16(v - hi); returns {hi01, hi23, lo01, lo23}
+// ---- split-fp16 mode: 4 fp32 channels of one pixel, fp32 blend with the reference's weights (1-ly)(1-lx), (1-ly)lx,
+// ly(1-lx), ly*lx, then split into fp16 hi and lo = fp16(v - hi); out[t] = {hi01, hi23, lo01, lo23}
 __device__ __forceinline__ float sub_half(float v, uint32_t packed, int hi_half) {
     // v - float(half): one mixed-precision FMA (FHFMA) instead of a convert and a subtract; exact in fp32
     float d;
@@ -200,117 +188,28 @@ __device__ __forceinline__ unsigned long long f2fma(unsigned long long a, unsign
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
     return r;
 }
-template <int M>
-__device__ __forceinline__ uint4 blend_tap(const uint4& a, const uint4& b, const uint4& c, const uint4& d, const WtsF& W) {
-    // same operation order per channel as the scalar form: w00*a, then fma w01*b, w10*c, w11*d (each one rounding)
-    const unsigned long long w0 = f2bcast(W.w[M][0]), w1 = f2bcast(W.w[M][1]), w2 = f2bcast(W.w[M][2]), w3 = f2bcast(W.w[M][3]);
-    const unsigned long long v01 = f2fma(w3, f2pack(d.x, d.y), f2fma(w2, f2pack(c.x, c.y), f2fma(w1, f2pack(b.x, b.y), f2mul(w0, f2pack(a.x, a.y)))));
-    const unsigned long long v23 = f2fma(w3, f2pack(d.z, d.w), f2fma(w2, f2pack(c.z, c.w), f2fma(w1, f2pack(b.z, b.w), f2mul(w0, f2pack(a.z, a.w)))));
-    float v0, v1, v2, v3;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(v0), "=f"(v1) : "l"(v01));
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(v2), "=f"(v3) : "l"(v23));
-    return split4(v0, v1, v2, v3);
-}
-__device__ __forceinline__ uint4 centre_tap(const uint4& n, const WtsH&) { return n; }
-__device__ __forceinline__ uint4 centre_tap(const uint4& n, const WtsF&) {
-    return split4(__uint_as_float(n.x), __uint_as_float(n.y), __uint_as_float(n.z), __uint_as_float(n.w));
-}
-
-// One raster tap into tensor memory: fp16 = 8 channels in 4 columns; split-fp16 = 4 channels, hi in 2 columns, lo 72 further.
-__device__ __forceinline__ void store_tap(uint32_t cb, int t, const uint4& v, const WtsH&) { tmem_st4(cb + t * 8, v.x, v.y, v.z, v.w); }
-__device__ __forceinline__ void store_tap(uint32_t cb, int t, const uint4& v, const WtsF&) {
-    tmem_st2(cb + t * 8, v.x, v.y);
-    tmem_st2(cb + 72 + t * 8, v.z, v.w);
-}
-// raster tap (centre skipped) of rotated tap m for octant o
-__device__ __forceinline__ constexpr int raster_of(int m, int o) { return (((m - o) & 7) < 4) ? ((m - o) & 7) : ((m - o) & 7) + 1; }
-
-// One chunk of one pixel -> the 9 raster taps in tensor memory.  tcgen05.st needs the warp converged with one column
-// address, so the tap rotation lives in the CODE: this variant for a warp whose 32 pixels share octant O (everywhere
-// except along the 8 octant boundaries).  Rotated taps are visited in pairs that share their 2x2 cell (m = 0,1: centre /
-// right / below; 2,3: above / right; 4,5: above / left; 6,7: below / left) and the neighbours are loaded cell by cell -
-// ld.shared and tcgen05.st are volatile, so at most 6 of the 9 neighbours are live at a time (24 instead of 36 registers).
-template <int O, typename W>
-__device__ __forceinline__ void item_uniform(uint32_t hbase, const Lines& nl, uint32_t cx, uint32_t cb, const W& w) {
-    const uint4 n4 = lds128(hbase + (nl.l[4] ^ cx)), n5 = lds128(hbase + (nl.l[5] ^ cx));
-    const uint4 n7 = lds128(hbase + (nl.l[7] ^ cx)), n8 = lds128(hbase + (nl.l[8] ^ cx));
-    store_tap(cb, 4, centre_tap(n4, w), w);
-    store_tap(cb, raster_of(0, O), blend_tap<0>(n4, n5, n7, n8, w), w);
-    store_tap(cb, raster_of(1, O), blend_tap<1>(n4, n5, n7, n8, w), w);
-    const uint4 n1 = lds128(hbase + (nl.l[1] ^ cx)), n2 = lds128(hbase + (nl.l[2] ^ cx));
-    store_tap(cb, raster_of(2, O), blend_tap<2>(n1, n2, n4, n5, w), w);
-    store_tap(cb, raster_of(3, O), blend_tap<3>(n1, n2, n4, n5, w), w);
-    const uint4 n0 = lds128(hbase + (nl.l[0] ^ cx)), n3 = lds128(hbase + (nl.l[3] ^ cx));
-    store_tap(cb, raster_of(4, O), blend_tap<4>(n0, n1, n3, n4, w), w);
-    store_tap(cb, raster_of(5, O), blend_tap<5>(n0, n1, n3, n4, w), w);
-    const uint4 n6 = lds128(hbase + (nl.l[6] ^ cx));
-    store_tap(cb, raster_of(6, O), blend_tap<6>(n3, n4, n6, n7, w), w);
-    store_tap(cb, raster_of(7, O), blend_tap<7>(n3, n4, n6, n7, w), w);
-}
-template <typename W>
-__device__ __forceinline__ void item_uniform_any(int oct, uint32_t hbase, const Lines& nl, uint32_t cx, uint32_t cb, const W& w) {
-    switch (oct) {
-        case 0: item_uniform<0>(hbase, nl, cx, cb, w); break;
-        case 1: item_uniform<1>(hbase, nl, cx, cb, w); break;
-        case 2: item_uniform<2>(hbase, nl, cx, cb, w); break;
-        case 3: item_uniform<3>(hbase, nl, cx, cb, w); break;
-        case 4: item_uniform<4>(hbase, nl, cx, cb, w); break;
-        case 5: item_uniform<5>(hbase, nl, cx, cb, w); break;
-        case 6: item_uniform<6>(hbase, nl, cx, cb, w); break;
-        default: item_uniform<7>(hbase, nl, cx, cb, w); break;
-    }
-}
-// A warp that straddles an octant boundary (6 % of the warps at 512x512, 25 % at 128x128): the variant is selected per lane
-// and per raster tap, the warp reconverges before every store (a warp with two octants runs every tap twice).  Not
-// inlined: the 9 live neighbours (36 registers) stay out of the common path's register budget.
-template <int O, int T, typename W>
-__device__ __forceinline__ uint4 tap_of(const uint4 (&nb)[9], const W& w) {
-    constexpr int kq = T < 4 ? T : T - 1;
-    constexpr int m = (kq + O) & 7;
-    constexpr int r0 = tm_r0(m), c0 = tm_c0(m);
-    return blend_tap<m>(nb[r0 * 3 + c0], nb[r0 * 3 + c0 + 1], nb[(r0 + 1) * 3 + c0], nb[(r0 + 1) * 3 + c0 + 1], w);
-}
-template <int T, typename W>
-__device__ __forceinline__ void tap_mixed(uint32_t cb, int oct, const uint4 (&nb)[9], const W& w) {
-    uint4 v;
-    switch (oct) {
-        case 0: v = tap_of<0, T>(nb, w); break;
-        case 1: v = tap_of<1, T>(nb, w); break;
-        case 2: v = tap_of<2, T>(nb, w); break;
-        case 3: v = tap_of<3, T>(nb, w); break;
-        case 4: v = tap_of<4, T>(nb, w); break;
-        case 5: v = tap_of<5, T>(nb, w); break;
-        case 6: v = tap_of<6, T>(nb, w); break;
-        default: v = tap_of<7, T>(nb, w); break;
-    }
-    __syncwarp();
-    store_tap(cb, T, v, w);
-}
-template <typename W>
-__device__ __noinline__ void item_mixed(int oct, uint32_t hbase, Lines nl, uint32_t cx, uint32_t cb, W w) {
-    uint4 nb[9];
+template <int O>
+__device__ __forceinline__ void blend_f(const uint4 (&nb)[9], const float (&w)[8][4], uint4 (&out)[9]) {
+    out[4] = split4(__uint_as_float(nb[4].x), __uint_as_float(nb[4].y), __uint_as_float(nb[4].z), __uint_as_float(nb[4].w));
 #pragma unroll
-    for (int k = 0; k < 9; ++k) nb[k] = lds128(hbase + (nl.l[k] ^ cx));
-    store_tap(cb, 4, centre_tap(nb[4], w), w);
-    tap_mixed<0>(cb, oct, nb, w); tap_mixed<1>(cb, oct, nb, w); tap_mixed<2>(cb, oct, nb, w); tap_mixed<3>(cb, oct, nb, w);
-    tap_mixed<5>(cb, oct, nb, w); tap_mixed<6>(cb, oct, nb, w); tap_mixed<7>(cb, oct, nb, w); tap_mixed<8>(cb, oct, nb, w);
+    for (int t = 0; t < 9; ++t) {
+        if (t == 4) continue;
+        const int kq = t < 4 ? t : t - 1;
+        const int m = (kq + O) & 7;
+        const int r0 = tm_r0(m), c0 = tm_c0(m);
+        const uint4 &a = nb[r0 * 3 + c0], &b = nb[r0 * 3 + c0 + 1], &c = nb[(r0 + 1) * 3 + c0], &d = nb[(r0 + 1) * 3 + c0 + 1];
+        // same operation order per channel as the scalar form: w00*a, then fma w01*b, w10*c, w11*d (each one rounding)
+        const unsigned long long w0 = f2bcast(w[m][0]), w1 = f2bcast(w[m][1]), w2 = f2bcast(w[m][2]), w3 = f2bcast(w[m][3]);
+        const unsigned long long v01 = f2fma(w3, f2pack(d.x, d.y), f2fma(w2, f2pack(c.x, c.y), f2fma(w1, f2pack(b.x, b.y), f2mul(w0, f2pack(a.x, a.y)))));
+        const unsigned long long v23 = f2fma(w3, f2pack(d.z, d.w), f2fma(w2, f2pack(c.z, c.w), f2fma(w1, f2pack(b.z, b.w), f2mul(w0, f2pack(a.z, a.w)))));
+        float v0, v1, v2, v3;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(v0), "=f"(v1) : "l"(v01));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(v2), "=f"(v3) : "l"(v23));
+        out[t] = split4(v0, v1, v2, v3);
+    }
 }
 
 }  // namespace
-
-// Drain this warp's column batches of one accumulator set, zero them again (every MMA accumulates) and leave.  Not inlined
-// on purpose: its ~90 live registers would otherwise be added to the producer's per-tile state in the hot loop.  `p` must
-// point to the SHARED-MEMORY copy of the parameters: through a reference to the kernel's parameter block every field
-// access in here became a generic load from param space (no constant cache) - 4.5 kclk per 32-column batch.
-__device__ __noinline__ void tm_epilogue(const ConvParams& p, const float* s_par, uint32_t t_acc, int n, int oy, int ox, int ci, int epw,
-                                         bool tail) {
-    // stage 1 only needs the plain variants (no activation / ReLU / LeakyReLU; never a second affine or a lo plane)
-    epilogue_row<0x0007u, false, false>(p, s_par, t_acc, n, oy, ox, ci, 1, 0, epw);      // 128-bit stores (see store32)
-    __syncwarp();                // tcgen05.st is warp-collective
-    for (int cbi = tail ? 0 : ci; cbi < p.Cout / 32; cbi += epw) tmem_st_zero32(t_acc + static_cast<uint32_t>(cbi * 32));
-    tmem_st_wait();
-    tc_fence_before();
-}
 
 template <bool kExact>
 __global__ void __launch_bounds__(kTmThreads, 1)
@@ -337,11 +236,9 @@ conv_ric_tm_kernel(const __grid_constant__ TmParams P) {
     const int tiles_per_frame = tiles_x * tiles_y;
     const int total_tiles = tiles_per_frame * p.B;
     const int my_tiles = (total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-    constexpr int kWarpIss0 = kTmProducerWarps, kWarpHalo = kWarpIss0 + kTmIssuerWarps;
-    // epilogue: the conv_12 tail needs a whole accumulator row in one thread, otherwise the C / 32 column batches are
-    // dealt round-robin to the (up to) four warps of a lane quadrant
-    const bool tail = p.epi.w12 != nullptr;
-    const int EPW = tail ? 1 : (C / 32 < 3 ? C / 32 : 3);
+    constexpr int kEpi = kTmEpilogueWarps * 32;
+    constexpr int kWarpEpi0 = kTmProducerWarps, kWarpIss0 = kWarpEpi0 + kTmEpilogueWarps, kWarpHalo = kWarpIss0 + kTmIssuerWarps,
+                  kWarpWgt = kWarpHalo + 1;
 
     if (warp == kWarpIss0) {
         if (lane == 0) {
@@ -349,9 +246,9 @@ conv_ric_tm_kernel(const __grid_constant__ TmParams P) {
                 mbar_init(bar_halo_full + 8 * s, 1);
                 mbar_init(bar_halo_empty + 8 * s, kTmProducerWarps);
                 mbar_init(bar_acc_full + 8 * s, NI);
-                mbar_init(bar_acc_empty + 8 * s, 4 * EPW * 32);
+                mbar_init(bar_acc_empty + 8 * s, kEpi);
             }
-            for (int s = 0; s < 3; ++s) mbar_init(bar_a_full + 8 * s, 16);        // one arrival per (quadrant, chunk)
+            for (int s = 0; s < 3; ++s) mbar_init(bar_a_full + 8 * s, kTmProducerWarps);
             for (int s = 0; s < kTmMaxB; ++s) {
                 mbar_init(bar_b_full + 8 * s, 1);
                 mbar_init(bar_done + 8 * s, NI);
@@ -361,11 +258,8 @@ conv_ric_tm_kernel(const __grid_constant__ TmParams P) {
         __syncwarp();
         tmem_alloc(smem_u32(tmem_slot), 512);
         tmem_relinquish();
-    } else if (warp < 4) {
-        load_epilogue_params(p, s_par, tid, 128);
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(&P.c);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(smem + L.pcopy);
-        for (int i = tid; i < static_cast<int>(sizeof(ConvParams) / 4); i += 128) dst[i] = src[i];
+    } else if (warp >= kWarpEpi0 && warp < kWarpIss0) {
+        load_epilogue_params(p, s_par, tid - kWarpEpi0 * 32, kEpi);
     } else if (warp == kWarpHalo && lane == 0) {
         for (int i = 0; i < kTmMaxMaps; ++i) tma_prefetch_desc(&P.tmap[i]);
     }
@@ -384,55 +278,17 @@ conv_ric_tm_kernel(const __grid_constant__ TmParams P) {
     };
 
     if (warp < kTmProducerWarps) {
-        // ================================================================ producers + epilogue
-        // CTA register pool: the 8 light warps release (96 - 48) x 32 each = 12288 = 12 x (128 - 96) x 32
-        reg_inc<128>();
-        const int wk = warp >> 2;                                    // 0..2: item (stage j, chunk c) belongs to warp (4 j + c) % 3
-        const int ci = wk;                                           // column batches ci, ci + EPW, .. of the epilogue
-        const int quad = warp & 3;
-        const int r = quad * 32 + lane;                              // tile pixel = accumulator row = TMEM lane
+        // ================================================================ producers
+        reg_inc<144>();      // CTA register pool: 8 light warps release (96 - 40) x 32 each = 14336 = 8 x (144 - 96) x 32 + 4 x (112 - 96) x 32
+        const int g = warp >> 2;                                     // chunk pair of a stage this warp produces
+        const int r = (warp & 3) * 32 + lane;                        // tile pixel = accumulator row = TMEM lane
         const int py = r >> 4, px = r & 15;
-        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
         const uint32_t halo_u32 = base + L.halo0;
         int j = 0, gb = 0;                                           // stages / blocks produced so far by this CTA
-        int c0 = wk;                                                 // this warp's first chunk of stage j: (wk - j) mod 3; the second is c0 + 3
-        Ring ra, rd, rs;                                             // A stage being written; completion of step j - SA; accumulator set
-#ifdef DSU_TM_TRACE_PRODUCERS            // costs ~6 registers in the hot loop: compiled in only for timeline studies
-        Trace tr, tre;
+        Ring ra, rd;                                                 // A stage being written; completion barrier of step j - SA
+        Trace tr;
         tr.init(P.trace, 0, blockIdx.x == 0 && tid == 0);
-        tre.init(P.trace, 2, blockIdx.x == 0 && tid == 0);
-#define DSU_TR(obj, id, a) obj.ev(id, a)
-#else
-#define DSU_TR(obj, id, a) ((void)0)
-#endif
-
-        // accumulators start as zeros (every MMA accumulates) and are zeroed again by whoever drains them
-        if (ci < EPW) {
-            for (int s = 0; s < NSETS; ++s) {
-                for (int cbi = tail ? 0 : ci; cbi < C / 32; cbi += EPW) tmem_st_zero32(lane_addr + static_cast<uint32_t>(s * C + cbi * 32));
-                tmem_st_wait();
-                tc_fence_before();
-                mbar_arrive(bar_acc_empty + 8 * s);
-            }
-        }
-        // epilogue of one finished tile: drain this warp's column batches, zero them, hand the set back to the issuers
-        auto epilogue = [&](int eit, int en, int ety0, int etx0) {
-            const int set = rs.idx;
-            const uint32_t ph = rs.phase;
-            rs.advance(NSETS);
-            if (ci >= EPW) return;
-            mbar_wait_wd<0>(bar_acc_full + 8 * set, ph, P.dbg, 3, eit, set);
-            tc_fence_after();
-            DSU_TR(tre, 5, eit);
-            const uint32_t t_acc = lane_addr + static_cast<uint32_t>(set * C);
-            tm_epilogue(*reinterpret_cast<const ConvParams*>(smem + L.pcopy), s_par, t_acc, en, ety0 + (r >> 4), etx0 + (r & 15), ci, EPW, tail);
-            mbar_arrive(bar_acc_empty + 8 * set);
-            DSU_TR(tre, 6, eit);
-        };
-        bool pending = false;
-        int pn = 0, pty0 = 0, ptx0 = 0;
-        const int epi_after = P.nstages < 2 ? P.nstages : 2;         // stages of the next tile produced before the epilogue
-
         for (int it = 0; it < my_tiles; ++it) {
             int n, ty0, tx0;
             tile_coords(it, n, ty0, tx0);
@@ -441,14 +297,13 @@ conv_ric_tm_kernel(const __grid_constant__ TmParams P) {
             const size_t e = live ? static_cast<size_t>(oy) * p.Wout + ox : 0;
             // ---- per-pixel state for the whole tile
             const int oct = __ldg(p.ric_oct + e);
-            const bool uniform = __all_sync(0xffffffffu, oct == __shfl_sync(0xffffffffu, oct, 0));
-            typename std::conditional<kExact, WtsF, WtsH>::type wt;   // the pixel's bilinear weights, rotated tap order
+            uint4 wq[4];                                             // fp16 mode: 8 x {w00,w01 | w10,w11}
+            float w[8][4];                                           // split-fp16 mode: fp32 weights in rotated tap order
             if constexpr (!kExact) {
                 const uint4* tp = reinterpret_cast<const uint4*>(p.ric_wh + e * 8);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) wt.q[i] = __ldg(tp + i);
+                for (int i = 0; i < 4; ++i) wq[i] = __ldg(tp + i);
             } else {
-                float (&w)[8][4] = wt.w;
                 const float4* tp = reinterpret_cast<const float4*>(p.ric_lyx + e * 8);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -461,9 +316,8 @@ conv_ric_tm_kernel(const __grid_constant__ TmParams P) {
             }
             // neighbour (dy, dx) -> 128-byte line of the halo tile (source pixel, nearest x2 folded in) with its swizzle key in
             // bits 4-6: the 16-byte chunk c of that pixel sits at line * 128 + ((c ^ (line & 7)) << 4)  (TMA SWIZZLE_128B)
-            Lines nl;
+            uint32_t nbl[9];
             {
-                uint32_t (&nbl)[9] = nl.l;
                 const int sy0 = (ty0 - 1) >> p.up, sx0 = (tx0 - 1) >> p.up;
 #pragma unroll
                 for (int dy = 0; dy < 3; ++dy)
@@ -473,7 +327,6 @@ conv_ric_tm_kernel(const __grid_constant__ TmParams P) {
                         nbl[dy * 3 + dx] = static_cast<uint32_t>(line) * 128u + (static_cast<uint32_t>(line & 7) << 4);
                     }
             }
-            int produced = 0;
             for (int b = 0; b < P.nblocks; ++b, ++gb) {
                 const TmBlock blk = P.blk[b];
                 const int hb = gb & 1;
@@ -487,47 +340,116 @@ conv_ric_tm_kernel(const __grid_constant__ TmParams P) {
                         tc_fence_after();
                     }
                     ra.advance(SA);
-                    DSU_TR(tr, 1, j);
-                    // this warp's chunks of the stage (chunk of the line = 4 * h + c).  fp16: 8 channels = 4 columns of K16 step
-                    // c >> 1 at (c >> 1) * 72 + tap * 8 + (c & 1) * 4; split-fp16: 4 channels = 2 columns at tap * 8 + c * 2 (lo + 72)
-                    const uint32_t sbase = lane_addr + a_col0 + static_cast<uint32_t>(slot * kTmStageCols);
-                    int nmine = 0;
+                    tr.ev(1, j);
+                    const uint32_t col0 = a_col0 + static_cast<uint32_t>(slot * kTmStageCols);
+                    const int nvalid = blk.chunks[h];
 #pragma unroll 1
-                    for (int c = c0; c < 4; c += 3, ++nmine) {
-                        const uint32_t cb = sbase + static_cast<uint32_t>(kExact ? c * 2 : (c >> 1) * 72 + (c & 1) * 4);
-                        if (c >= blk.chunks[h]) {                    // K padding of a ragged last stage: the MMA reads these columns
+                    for (int u = 0; u < 2; ++u) {
+                        const int ci = 2 * g + u;                    // chunk of the stage; chunk of the line = 4 * h + ci
+                        if (ci >= nvalid) {                          // K padding of a ragged last stage: the MMA reads these columns
+                            if constexpr (!kExact) {
+                                const uint32_t cb = lane_addr + col0 + static_cast<uint32_t>((ci >> 1) * 72 + (ci & 1) * 4);
+#pragma unroll
+                                for (int t = 0; t < 9; ++t) tmem_st4(cb + t * 8, 0u, 0u, 0u, 0u);
+                            } else {
+                                const uint32_t cb = lane_addr + col0 + static_cast<uint32_t>(ci * 2);
+#pragma unroll
+                                for (int t = 0; t < 9; ++t) { tmem_st2(cb + t * 8, 0u, 0u); tmem_st2(cb + 72 + t * 8, 0u, 0u); }
+                            }
+                            continue;
+                        }
+                        uint4 out[9];
+                        {
+                            const uint32_t cx = static_cast<uint32_t>(4 * h + ci) << 4;
+                            uint4 nb[9];
+#pragma unroll
+                            for (int k = 0; k < 9; ++k) nb[k] = lds128(hbase + (nbl[k] ^ cx));
+                            if constexpr (!kExact) {
+                                switch (oct) {
+                                    case 0: blend_h<0>(nb, wq, out); break;
+                                    case 1: blend_h<1>(nb, wq, out); break;
+                                    case 2: blend_h<2>(nb, wq, out); break;
+                                    case 3: blend_h<3>(nb, wq, out); break;
+                                    case 4: blend_h<4>(nb, wq, out); break;
+                                    case 5: blend_h<5>(nb, wq, out); break;
+                                    case 6: blend_h<6>(nb, wq, out); break;
+                                    default: blend_h<7>(nb, wq, out); break;
+                                }
+                            } else {
+                                switch (oct) {
+                                    case 0: blend_f<0>(nb, w, out); break;
+                                    case 1: blend_f<1>(nb, w, out); break;
+                                    case 2: blend_f<2>(nb, w, out); break;
+                                    case 3: blend_f<3>(nb, w, out); break;
+                                    case 4: blend_f<4>(nb, w, out); break;
+                                    case 5: blend_f<5>(nb, w, out); break;
+                                    case 6: blend_f<6>(nb, w, out); break;
+                                    default: blend_f<7>(nb, w, out); break;
+                                }
+                            }
+                        }
+                        __syncwarp();                                // reconverge before the warp-collective stores
+                        if constexpr (!kExact) {
+                            // 8 channels = 4 columns of K16 step ci >> 1: tap t at col0 + (ci >> 1) * 72 + t * 8 + (ci & 1) * 4
+                            const uint32_t cb = lane_addr + col0 + static_cast<uint32_t>((ci >> 1) * 72 + (ci & 1) * 4);
+#pragma unroll
+                            for (int t = 0; t < 9; ++t) tmem_st4(cb + t * 8, out[t].x, out[t].y, out[t].z, out[t].w);
+                        } else {
+                            // 4 channels = 2 columns: hi at col0 + t * 8 + ci * 2, lo 72 columns further
+                            const uint32_t cb = lane_addr + col0 + static_cast<uint32_t>(ci * 2);
 #pragma unroll
                             for (int t = 0; t < 9; ++t) {
-                                if constexpr (!kExact) tmem_st4(cb + t * 8, 0u, 0u, 0u, 0u);
-                                else { tmem_st2(cb + t * 8, 0u, 0u); tmem_st2(cb + 72 + t * 8, 0u, 0u); }
+                                tmem_st2(cb + t * 8, out[t].x, out[t].y);
+                                tmem_st2(cb + 72 + t * 8, out[t].z, out[t].w);
                             }
-                        } else {
-                            const uint32_t cx = static_cast<uint32_t>(4 * h + c) << 4;
-                            if (uniform) item_uniform_any(oct, hbase, nl, cx, cb, wt);
-                            else item_mixed(oct, hbase, nl, cx, cb, wt);
                         }
                     }
-                    c0 = c0 == 0 ? 2 : c0 - 1;                       // (wk - (j + 1)) mod 3
                     tmem_st_wait();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_n(bar_a_full + 8 * slot, static_cast<uint32_t>(nmine));
-                    DSU_TR(tr, 2, j);
-                    // the previous tile is drained once two stages of this one are on their way: its last MMAs finish meanwhile
-                    if (pending && ++produced == epi_after) {
-                        epilogue(it - 1, pn, pty0, ptx0);
-                        pending = false;
-                    }
+                    if (lane == 0) mbar_arrive(bar_a_full + 8 * slot);
+                    tr.ev(2, j);
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_halo_empty + 8 * hb);    // this warp has read the halo tile for the last time
             }
-            pending = true;
-            pn = n; pty0 = ty0; ptx0 = tx0;
         }
-        if (pending) epilogue(my_tiles - 1, pn, pty0, ptx0);
+    } else if (warp < kWarpIss0) {
+        // ================================================================ epilogue (one warp per TMEM lane quadrant)
+        reg_inc<112>();
+        const int quad = warp - kWarpEpi0;
+        const int r = quad * 32 + lane;
+        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+        // every MMA accumulates: the accumulators start as zeros and are zeroed again after each drain
+        for (int s = 0; s < NSETS; ++s) {
+            for (int c = 0; c < C; c += 32) tmem_st_zero32(lane_addr + static_cast<uint32_t>(s * C + c));
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(bar_acc_empty + 8 * s);
+        }
+        Ring rs;
+        Trace tr;
+        tr.init(P.trace, 2, blockIdx.x == 0 && tid == kWarpEpi0 * 32);
+        for (int it = 0; it < my_tiles; ++it) {
+            int n, ty0, tx0;
+            tile_coords(it, n, ty0, tx0);
+            const int set = rs.idx;
+            mbar_wait_wd<256>(bar_acc_full + 8 * set, rs.phase, P.dbg, 3, it, set);
+            tr.ev(5, it);
+            rs.advance(NSETS);
+            tc_fence_after();
+            const uint32_t t_acc = lane_addr + static_cast<uint32_t>(set * C);
+            // stage 1 only needs the plain variants (no activation / ReLU / LeakyReLU; never a second affine or a lo plane)
+            epilogue_row<0x0007u>(p, s_par, t_acc, n, ty0 + (r >> 4), tx0 + (r & 15), 0, 1, 0, 1);
+            tr.ev(8, it);
+            for (int c = 0; c < C; c += 32) tmem_st_zero32(t_acc + c);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(bar_acc_empty + 8 * set);
+            tr.ev(6, it);
+        }
     } else {
-        reg_dec<48>();
+        reg_dec<40>();
         if (warp < kWarpHalo) {
             // ============================================================ MMA issuers: MMA q of a stage goes to issuer q % NI
             const int wi = warp - kWarpIss0;
@@ -540,7 +462,7 @@ conv_ric_tm_kernel(const __grid_constant__ TmParams P) {
                 tr.init(P.trace, 1, blockIdx.x == 0 && tid == kWarpIss0 * 32);
                 for (int it = 0; it < my_tiles; ++it) {
                     const int set = rs.idx;
-                    mbar_wait_wd<0>(bar_acc_empty + 8 * set, rs.phase, P.dbg, 4, it, set);         // drained and zeroed
+                    mbar_wait_wd<96>(bar_acc_empty + 8 * set, rs.phase, P.dbg, 4, it, set);        // drained and zeroed
                     rs.advance(NSETS);
                     tc_fence_after();
                     const uint32_t d_addr = tmem_base + static_cast<uint32_t>(set * C);
@@ -551,8 +473,8 @@ conv_ric_tm_kernel(const __grid_constant__ TmParams P) {
                             // fp16: parts = live K16 steps (2 chunks each); split-fp16: hi*Whi, lo*Whi, hi*Wlo of one K16 step
                             const int nparts = kExact ? 3 : (blk.chunks[h] + 1) >> 1;
                             const int nq = 9 * nparts;
-                            mbar_wait_wd<0>(bar_b_full + 8 * sb, rb.phase, P.dbg, 5, j, it);
-                            mbar_wait_wd<0>(bar_a_full + 8 * slot, ra.phase, P.dbg, 6, j, it);
+                            mbar_wait_wd<32>(bar_b_full + 8 * sb, rb.phase, P.dbg, 5, j, it);
+                            mbar_wait_wd<32>(bar_a_full + 8 * slot, ra.phase, P.dbg, 6, j, it);
                             ra.advance(SA);
                             rb.advance(SB);
                             tc_fence_after();
