@@ -95,6 +95,11 @@ struct ConvParams {
     // is staged once and every tap reads a shifted window of it through the UMMA descriptor
     int halo, ns, ks, ksize, pad, halo_w, halo_rows, halo_bytes;   // ks: K-split issuers per sub-tile
     int tps;                // persistent halo kernel: taps per weight stage (one bulk copy / one commit per tps taps)
+    // split-fp16 halo layers with Cout = 64: the weight tile of a (tap, 32-channel block) is a no-swizzle K-major tile of 128
+    // rows [W_hi (64) ; W_lo (64)] x 32 channels, so a_hi x [W_hi | W_lo] is ONE N = 128 MMA (64 cycles, inside the shared-
+    // memory operand bandwidth) and a_lo x W_hi one N = 64 MMA on the first 64 rows: 113 instead of 3 x 49 cycles per K16
+    // step.  Accumulator = 128 columns per issuer (hi.W_hi + lo.W_hi | hi.W_lo), summed by the epilogue.  nsets: 1 or 2.
+    int n128, nsets;
     const Slot* slots;      // plain: [nchunks][8]; RIC: [nblocks][8]
     const uint8_t* wpack;   // pre-swizzled B tiles
     Seg seg[kMaxSeg];

@@ -109,6 +109,9 @@ conv_first_kernel(const __grid_constant__ ConvParams p) {
         const Slot sl0 = p.slots[0];                        // every valid slot reads the same 8-channel group
         const Seg sg = p.seg[sl0.seg];
         const __half* sbase = sg.ptr + sl0.choff;
+        // split-fp16: the lo plane of the same pixels goes to the second half of the halo buffer
+        const __half* sbase_lo = p.exact ? p.seg[sl0.seg + kMaxSeg / 2].ptr + sl0.choff : nullptr;
+        const uint32_t plane_bytes = static_cast<uint32_t>(HR) * 16u;
         const int LAG = NA >= 3 ? 2 : 1;
         auto publish = [&](int it) {                        // this thread's copies of tile `it` have landed
             fence_proxy_async_smem();
@@ -130,6 +133,7 @@ conv_first_kernel(const __grid_constant__ ConvParams p) {
                 const size_t pix = frame_in + static_cast<size_t>(vy) * p.Win + vx;
                 const __half* src = ok ? sbase + pix * sg.pitch : sbase;
                 cp_async16(dst0 + e * 16, src, ok ? 16u : 0u);
+                if (sbase_lo) cp_async16(dst0 + plane_bytes + e * 16, ok ? sbase_lo + pix * sg.pitch : sbase_lo, ok ? 16u : 0u);
             }
             cp_async_commit();
             if (it >= LAG) {
@@ -151,7 +155,8 @@ conv_first_kernel(const __grid_constant__ ConvParams p) {
             mbar_wait(bar_acc_full + 8 * set, (it / NSETS) & 1);
             tc_fence_after();
             const uint32_t t_set = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(set * NI * C);
-            epilogue_row<kEpiFp16>(p, s_par, t_set, n, ty0 + (r >> 3), tx0 + (r & 7), 0, NI, C, 1);
+            if (p.exact) epilogue_row<kEpiSplit>(p, s_par, t_set, n, ty0 + (r >> 3), tx0 + (r & 7), 0, NI, C, 1);
+            else epilogue_row<kEpiFp16>(p, s_par, t_set, n, ty0 + (r >> 3), tx0 + (r & 7), 0, NI, C, 1);
             tc_fence_before();
             mbar_arrive(bar_acc_empty + 8 * set);
         }
@@ -179,6 +184,8 @@ conv_first_kernel(const __grid_constant__ ConvParams p) {
                 tc_fence_after();
                 const uint32_t d_addr = tmem_base + static_cast<uint32_t>((set * NI + wi) * C);
                 const uint32_t h_addr = base + L.h0 + hs * p.halo_bytes;
+                const uint32_t lo_off = static_cast<uint32_t>(p.halo_rows) * kPitch;     // lo plane of the halo tile (split-fp16)
+                const uint32_t wlo_off = static_cast<uint32_t>(C) * 128u;                // W_lo tile of a kernel row
                 uint32_t acc = 0;
                 for (int kh = wi; kh < KR; kh += NI) {
                     const uint32_t a_addr = h_addr + kh * kPitch;
@@ -190,6 +197,15 @@ conv_first_kernel(const __grid_constant__ ConvParams p) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             if ((km >> k) & 1) { umma_f16(d_addr, da0 + 2 * k, db0 + 2 * k, idesc, a2); a2 = 1u; }
+                        if (p.exact) {                      // + a_lo x W_hi + a_hi x W_lo
+                            const uint64_t dal = umma_desc_noswizzle(a_addr + lo_off, 16, kPitch), dbl = umma_desc_sw128(b_addr + wlo_off, 1024);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if ((km >> k) & 1) {
+                                    umma_f16(d_addr, dal + 2 * k, db0 + 2 * k, idesc, 1u);
+                                    umma_f16(d_addr, da0 + 2 * k, dbl + 2 * k, idesc, 1u);
+                                }
+                        }
                     }
                     acc = 1u;
                     __syncwarp();
@@ -215,7 +231,7 @@ size_t conv_first_smem_bytes(const ConvParams& p) {
     return first_smem(p.sa, p.halo_bytes, p.nchunks, p.b_bytes, p.Cout).total + 1024;
 }
 
-// Expects: fp16 mode, stride 1, no fused upsampling, one weight chunk per kernel row (slot j of chunk kh = tap (kh, j),
+// Expects: stride 1 (split-fp16: second halo plane + a W_lo tile behind every W_hi tile, 3 MMAs per K step), no fused upsampling, one weight chunk per kernel row (slot j of chunk kh = tap (kh, j),
 // all on the same 8-channel group), ksize <= 8, p.ks = issuers (1..4, <= ksize), p.sa = halo buffers (2..6),
 // p.ns = accumulator sets (2 or 4), p.halo_rows = 16 + ksize - 1, p.halo_bytes >= halo_rows * 256,
 // p.tmem_cols >= p.ns * p.ks * Cout.
@@ -231,9 +247,9 @@ cudaError_t launch_conv_first(const ConvParams& p, cudaStream_t stream) {
         if (e != cudaSuccess) return e;
         attr_set[dev] = true;
     }
-    if (p.exact || p.stride != 1 || p.up != 0 || p.ric || p.ksize < 1 || p.ksize > 8 || p.nchunks != p.ksize || p.pad != (p.ksize - 1) / 2 ||
+    if (p.stride != 1 || p.up != 0 || p.ric || p.ksize < 1 || p.ksize > 8 || p.nchunks != p.ksize || p.pad != (p.ksize - 1) / 2 ||
         p.sa < 2 || p.sa > kFirstMaxHalo || p.ks < 1 || p.ks > kFirstIssuers || p.ks > p.ksize || (p.ns != 2 && p.ns != 4) || p.ns * p.ks * p.Cout > 512 ||
-        p.tmem_cols < p.ns * p.ks * p.Cout || p.halo_rows != 16 + p.ksize - 1 || p.halo_bytes < p.halo_rows * kFirstHaloW * 16 ||
+        p.tmem_cols < p.ns * p.ks * p.Cout || p.halo_rows != 16 + p.ksize - 1 || p.halo_bytes < p.halo_rows * kFirstHaloW * 16 * (p.exact ? 2 : 1) || p.b_bytes != p.Cout * 128 * (p.exact ? 2 : 1) ||
         (p.halo_bytes & 127) || p.kmask_full != p.kmask_last || conv_first_smem_bytes(p) > 227 * 1024)
         return cudaErrorInvalidConfiguration;
     const int tiles = ((p.Wout + 7) / 8) * ((p.Hout + 15) / 16) * p.B;

@@ -6,7 +6,8 @@
 // prologue + epilogue than in its main loop (profiles/: conv_11_a 0.9 -> see DESIGN.md section 7).
 //
 // Roles: warps 0-3 halo producers, warps 4-7 epilogue, warps 8-11 MMA issuers (sub-tile x K-split, private
-// weight rings - see conv_halo.cu), warp 12 weight loader.  TMEM: 2 sets x (ns*ks) accumulators x Cout columns.
+// weight rings - see conv_halo.cu), warp 12 weight loader.  TMEM: nsets (2, or 1 when two do not fit) x (ns*ks) accumulators
+// x Cout columns (2 Cout in the n128 form of the split-fp16 Cout = 64 layers, see ConvParams::n128).
 #include "conv_device.cuh"
 
 namespace dsu {
@@ -43,6 +44,8 @@ conv_halo_persist_kernel(const __grid_constant__ ConvParams p) {
     uint8_t* smem = smem_raw + (base - raw_u32);
     const int NA = p.sa, SB = p.sb, C = p.Cout, NS = p.ns, KS = p.ks;
     const int NI = NS * KS;
+    const int AC = p.n128 ? 2 * C : C;                         // accumulator columns per issuer
+    const int NSETS = p.nsets;
     const int SBK = SB / KS;
     const int TPS = p.tps;                                   // taps per weight stage (> 1 only with ks == 1)
     const int stage_bytes = TPS * p.b_bytes;
@@ -135,17 +138,21 @@ conv_halo_persist_kernel(const __grid_constant__ ConvParams p) {
         // ======================================================== epilogue warps (one per TMEM lane quadrant)
         const int quad = warp - 4;
         const int r = quad * 32 + lane;
+        int set = 0;
+        uint32_t sph = 0;                                // accumulator set of tile `it` and the phase of its barriers
         for (int it = 0; it < my_tiles; ++it) {
             int n, ty0, tx0;
             tile_coords(it, n, ty0, tx0);
-            const int set = it & 1;
-            mbar_wait(bar_acc_full + 8 * set, (it >> 1) & 1);
+            mbar_wait(bar_acc_full + 8 * set, sph);
             tc_fence_after();
-            const uint32_t t_set = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(set * NI * C);
-            for (int s = 0; s < NS; ++s)
-                epilogue_row<kEpiAll, kSub>(p, s_par, t_set + s * C, n, ty0 + (r >> 3), tx0 + 8 * s + (r & 7), 0, KS, NS * C, 1);
+            const uint32_t t_set = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(set * NI * AC);
+            for (int s = 0; s < NS; ++s) {
+                if (p.n128) epilogue_row<kEpiAll, kSub>(p, s_par, t_set + s * AC, n, ty0 + (r >> 3), tx0 + 8 * s + (r & 7), 0, 2, C, 1);
+                else epilogue_row<kEpiAll, kSub>(p, s_par, t_set + s * C, n, ty0 + (r >> 3), tx0 + 8 * s + (r & 7), 0, KS, NS * C, 1);
+            }
             tc_fence_before();
             mbar_arrive(bar_acc_empty + 8 * set);        // this accumulator set may be overwritten
+            if (++set == NSETS) { set = 0; sph ^= 1u; }
         }
     } else if (warp < 8 + kIssuersHalo) {
         // ======================================================== MMA issuers (warp-uniform loops, elected lane issues)
@@ -154,14 +161,16 @@ conv_halo_persist_kernel(const __grid_constant__ ConvParams p) {
             const int sub = wi % NS, ksp = wi / NS;
             const uint32_t idesc = umma_idesc_f16(kTileM, C);
             const uint32_t sbo = static_cast<uint32_t>(p.halo_w) * 128u;
+            const uint32_t idesc2 = umma_idesc_f16(kTileM, 2 * C);
             int g = 0, cnt = 0;
+            int set = 0;
+            uint32_t sph = 1;                            // phase of the PREVIOUS use of this set's empty barrier
             for (int it = 0; it < my_tiles; ++it) {
-                const int set = it & 1;
-                if (it >= 2) {                           // the epilogue of the tile that used this set must be done
-                    mbar_wait(bar_acc_empty + 8 * set, ((it >> 1) - 1) & 1);
+                if (it >= NSETS) {                       // the epilogue of the tile that used this set must be done
+                    mbar_wait(bar_acc_empty + 8 * set, sph);
                     tc_fence_after();
                 }
-                const uint32_t d_addr = tmem_base + static_cast<uint32_t>((set * NI + wi) * C);
+                const uint32_t d_addr = tmem_base + static_cast<uint32_t>((set * NI + wi) * AC);
                 uint32_t acc = 0;
                 for (int b = 0; b < p.nblocks; ++b, ++g) {
                     const int s_a = g % NA;
@@ -184,7 +193,18 @@ conv_halo_persist_kernel(const __grid_constant__ ConvParams p) {
                             if (elect_one()) {
                                 const uint64_t da0 = umma_desc_sw128(a_addr, sbo);
                                 const uint64_t db0 = umma_desc_sw128(b_addr, 1024);
-                                if (km2) {
+                                if (p.n128) {
+                                    // B tile [128 rows = W_hi ; W_lo][32 channels], no swizzle: K16 step k starts 256 B further
+                                    uint32_t a2 = acc;
+#pragma unroll
+                                    for (int k = 0; k < 2; ++k)
+                                        if ((km >> k) & 1) {
+                                            const uint64_t dbn = umma_desc_noswizzle(b_addr + k * 256, 128, 512);
+                                            umma_f16(d_addr, da0 + 2 * k, dbn, idesc2, a2);          // a_hi x [W_hi | W_lo]
+                                            umma_f16(d_addr, da0 + 4 + 2 * k, dbn, idesc, 1u);       // a_lo x W_hi
+                                            a2 = 1u;
+                                        }
+                                } else if (km2) {
                                     // split-fp16: A = [a_hi | a_lo] (steps 0-1 | 2-3), B = [W_hi | W_lo]; a_hi*W_hi + a_lo*W_hi + a_hi*W_lo
                                     uint32_t a2 = acc;
 #pragma unroll
@@ -218,6 +238,7 @@ conv_halo_persist_kernel(const __grid_constant__ ConvParams p) {
                     }
                     __syncwarp();
                 }
+                if (++set == NSETS) { set = 0; sph ^= 1u; }
             }
         }
         tc_fence_before();
@@ -269,8 +290,9 @@ cudaError_t launch_conv_halo_persist(const ConvParams& p, cudaStream_t stream) {
         attr_set[dev] = true;
     }
     if (p.sa < 1 || p.sa > kMaxHaloBufs || p.sb < 2 || p.sb > kMaxStagesB || p.ns < 1 || p.ks < 1 ||
-        p.ns * p.ks > kIssuersHalo || p.sb / p.ks < 2 || p.stride != 1 || 2 * p.ns * p.ks * p.Cout > 512 || p.tps < 1 || p.tps > 4 ||
-        p.tmem_cols < 2 * p.ns * p.ks * p.Cout || conv_halo_persist_smem_bytes(p) > 227 * 1024 ||
+        p.ns * p.ks > kIssuersHalo || p.sb / p.ks < 2 || p.stride != 1 || p.tps < 1 || p.tps > 4 || p.nsets < 1 || p.nsets > 2 ||
+        p.nsets * p.ns * p.ks * (p.n128 ? 2 : 1) * p.Cout > 512 || p.tmem_cols < p.nsets * p.ns * p.ks * (p.n128 ? 2 : 1) * p.Cout ||
+        (p.n128 && (p.ks != 1 || !p.exact || p.Cout != 64)) || conv_halo_persist_smem_bytes(p) > 227 * 1024 ||
         p.nchunks != p.nblocks * p.ksize * p.ksize || p.ks > p.ksize * p.ksize)
         return cudaErrorInvalidConfiguration;
     const int tiles = ((p.Wout + 8 * p.ns - 1) / (8 * p.ns)) * ((p.Hout + 15) / 16) * p.B;

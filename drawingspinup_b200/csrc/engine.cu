@@ -56,6 +56,8 @@ struct LayerDef {
     int out_buf = -1, out_choff = 0, out_relu = 0, out2_buf = -1;
     int resid_in = 0, resid_out = 0, final = 0;
     int halo = 0;          // plain stride-1 conv run by the halo-reuse kernel (conv_halo_persist.cu)
+    int b_bytes = 0;       // bytes of one chunk's weight tile(s) (0 = Cout x 128)
+    int n128 = 0;          // split-fp16 Cout = 64 halo layer packed for the N = 128 issue form (ConvParams::n128)
     int first = 0;         // one 8-channel group per tap, stride 1: im2col from a shared-memory halo (conv_first.cu)
     // experimental (DSU_SUBPIXEL=1): sub-pixel class py*2+px of a nearest-x2 + 3x3 convolution (models.py:180-192):
     // out(2y+py, 2x+px) = sum over a,b in {0,1} of Wc[a][b] * in(y+a-1+py, x+b-1+px), Wc = sums of the 3x3 taps that hit the
@@ -92,6 +94,8 @@ struct Knobs {
     int first_ks = 0, first_na = 0, first_sets = 0;
     int halo_persist = 2, halo_ns = 0, halo_ks = 0, halo_na = 0, halo_sb = 0, halo_tps = 0;
     int subpixel = 1;         // plan-time: stage-2 nearest-x2 + 3x3 as four 2x2 sub-pixel convolutions
+    int n128 = 2;             // plan-time: split-fp16 Cout = 64 halo layers issue a_hi x [W_hi | W_lo] as one N = 128 MMA: 2 = the 7x7 conv_11 only (measured: 12.8 -> 11.0 ms; the 3x3 smoothers lose 10-30 % without their second accumulator set), 1 = all, 0 = off
+    int halo_nsets = 0;       // 1 = force a single accumulator set in the persistent halo kernel (measurements)
     int tm_ni = 0, tm_sb = 0; // tensor-memory kernel: issuing warps / weight stages (0 = planner decides)
     int derive_edge = 0;      // stage 2, no edge map passed: burn the edges pos2edge finds in the pos frames (fused into the ingest)
     int tm_trace = 0;         // development: 1 + index of the launch step whose CTA 0 records an event trace (dsu_debug_watchdog slots 32..)
@@ -102,6 +106,7 @@ const KnobName kKnobNames[] = {
     {"first_sets", &Knobs::first_sets}, {"halo_persist", &Knobs::halo_persist}, {"halo_ns", &Knobs::halo_ns},
     {"halo_ks", &Knobs::halo_ks}, {"halo_na", &Knobs::halo_na}, {"halo_sb", &Knobs::halo_sb}, {"halo_tps", &Knobs::halo_tps},
     {"subpixel", &Knobs::subpixel}, {"tm_ni", &Knobs::tm_ni}, {"tm_sb", &Knobs::tm_sb}, {"tm_trace", &Knobs::tm_trace}, {"derive_edge", &Knobs::derive_edge},
+    {"n128", &Knobs::n128}, {"halo_nsets", &Knobs::halo_nsets},
 };
 Knobs knobs_from_env() {
     Knobs k;
@@ -471,11 +476,15 @@ int compile_layer(dsu_engine* E, LayerDef& L) {
     // halo-reuse kernel: plain stride-1 convs with >= 32 channels per tap (the 8-channel 7x7 conv0 was measured slower
     // there: 49 single-K-step MMAs per tile; it has its own kernel, conv_first.cu, and the tap-mode kernel as fallback)
     L.halo = (!L.ric && L.stride == 1 && real_k / (k * k) >= 32) ? 1 : 0;
+    // split-fp16, Cout = 64: [W_hi ; W_lo] x 32-channel no-swizzle tiles, a_hi x [W_hi | W_lo] as one N = 128 MMA (ConvParams::n128)
+    L.n128 = (L.halo && exact && C == 64 && (E->knobs.n128 == 1 || (E->knobs.n128 == 2 && k > 3))) ? 1 : 0;
     if (!L.ric && !L.halo) {
         // single 8-channel group per tap (conv0 of GeneratorJ), fp16 mode: one chunk per KERNEL ROW (slot j = tap (kh, j)),
         // the layout the im2col-free kernel (conv_first.cu) needs; the tap-mode kernel runs the same table
-        L.first = (!exact && L.stride == 1 && L.up == 0 && L.segs.size() == 1 && L.segs[0].nch <= 8 && k > 3 && k <= 8 &&
-                   L.pad == (k - 1) / 2) ? 1 : 0;
+        // split-fp16: the same kernel with a second (lo) halo plane and [W_hi ; W_lo] tile pairs per kernel row - a layout the
+        // tap-mode kernel cannot run, so there the choice is made here (knob `first`, plan-time) and not per launch
+        L.first = ((!exact || E->knobs.first != 0) && L.stride == 1 && L.up == 0 && L.segs.size() == 1 && L.segs[0].nch <= 8 && k > 3 &&
+                   k <= 8 && L.pad == (k - 1) / 2) ? 1 : 0;
         std::vector<HSlot> all;
         for (int kh = 0; kh < k; ++kh) {
             for (int kw = 0; kw < k; ++kw)
@@ -516,7 +525,9 @@ int compile_layer(dsu_engine* E, LayerDef& L) {
     }
     L.nchunks = static_cast<int>(chunks.size());
     std::vector<ChunkHdr> hdrs(L.nchunks);
-    const size_t tile = static_cast<size_t>(C) * 128;
+    const bool first_exact = L.first && exact;      // chunk = kernel row: a W_hi tile followed by a W_lo tile (8 tap slots each)
+    const size_t tile = static_cast<size_t>(C) * 128 * (first_exact ? 2 : 1);
+    L.b_bytes = static_cast<int>(tile);
     std::vector<uint8_t> pack(static_cast<size_t>(L.nchunks) * tile, 0);
     size_t off = 0;
     auto put = [&](size_t tile_off, int row, int slot, int ci, __half val) {
@@ -530,7 +541,7 @@ int compile_layer(dsu_engine* E, LayerDef& L) {
         ChunkHdr& hd = hdrs[q];
         hd.pad_ = 0;
         hd.b_off = static_cast<uint32_t>(off);
-        if (!exact) { hd.kmask = static_cast<uint8_t>((1 << steps) - 1); hd.kmask2 = 0; }
+        if (!exact || L.n128 || first_exact) { hd.kmask = static_cast<uint8_t>((1 << steps) - 1); hd.kmask2 = 0; }
         else { hd.kmask = static_cast<uint8_t>(((1 << steps) - 1) | (((1 << steps) - 1) << 2)); hd.kmask2 = static_cast<uint8_t>((1 << steps) - 1); }
         // B tile(s): row o = output channel, 128 B = 64 K elements, 16-byte slots XOR-swizzled by (row & 7)
         for (int o = 0; o < C; ++o)
@@ -539,8 +550,18 @@ int compile_layer(dsu_engine* E, LayerDef& L) {
                 for (int ci = 0; ci < h.nvalid; ++ci) {
                     const float wv = Wt[((static_cast<size_t>(o) * cin_total + h.wch + ci) * k + h.kh) * k + h.kw];
                     const __half wh = __float2half_rn(wv);
+                    if (L.n128) {
+                        // no-swizzle K-major tile of 128 rows x 32 channels: rows 0-63 W_hi, 64-127 W_lo; 8 x 16 B core matrices,
+                        // K-adjacent core matrices 128 B apart, 8-row groups 512 B apart
+                        const __half wl = __float2half_rn(wv - __half2float(wh));
+                        auto at = [&](int row) { return off + static_cast<size_t>(row / 8) * 512 + static_cast<size_t>(d) * 128 + (row % 8) * 16 + ci * 2; };
+                        std::memcpy(&pack[at(o)], &wh, 2);
+                        std::memcpy(&pack[at(o + 64)], &wl, 2);
+                        continue;
+                    }
                     put(off, o, d, ci, wh);
-                    if (exact) put(off, o, d + 4, ci, __float2half_rn(wv - __half2float(wh)));   // [W_hi | W_lo] in one row
+                    if (first_exact) put(off + static_cast<size_t>(C) * 128, o, d, ci, __float2half_rn(wv - __half2float(wh)));
+                    else if (exact) put(off, o, d + 4, ci, __float2half_rn(wv - __half2float(wh)));   // [W_hi | W_lo] in one row
                 }
             }
         off += tile;
@@ -790,7 +811,7 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
         p.up = L.up; p.Hv = p.Hin << L.up; p.Wv = p.Win << L.up;
         p.stride = L.stride; p.ric = L.ric; p.exact = E->exact ? 1 : 0;
         p.nchunks = L.nchunks; p.nblocks = L.nblocks; p.Cout = L.cout;
-        p.b_bytes = L.cout * 128;
+        p.b_bytes = L.b_bytes > 0 ? L.b_bytes : L.cout * 128;
         p.kmask_full = L.kmask_full; p.kmask_last = L.kmask_last; p.kmask2_full = L.kmask2_full; p.kmask2_last = L.kmask2_last;
         pick_stages(p.b_bytes, &p.sa, &p.sb);
         p.ks = 1;
@@ -871,15 +892,19 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
             // {sub-tiles, K-split issuers, halo buffers}
             static const int cand3[][3] = {{4, 1, 2}, {2, 2, 2}, {2, 1, 2}, {1, 2, 2}, {1, 1, 2}};
             static const int cand7[][3] = {{4, 1, 1}, {2, 2, 2}, {2, 1, 2}, {1, 2, 2}, {1, 1, 2}};
-            const int (*cand)[3] = kk <= 3 ? cand3 : cand7;
+            static const int cand3n[][3] = {{2, 1, 2}, {4, 1, 2}, {1, 1, 2}, {1, 1, 2}, {1, 1, 2}};   // n128 form: two accumulator sets first
+            const int (*cand)[3] = kk <= 3 ? (L.n128 ? cand3n : cand3) : cand7;
             const int persist_mode = K.halo_persist;   // 0 never, 1 when the chosen config allows, 2 prefer (measured best)
             const int env_ns = K.halo_ns > 0 ? std::min(4, K.halo_ns) : 0, env_ks = K.halo_ks > 0 ? std::min(4, K.halo_ks) : 0;
             const int env_na = K.halo_na > 0 ? std::min(3, K.halo_na) : 0;
             bool found = false;
+            const int acw = L.n128 ? 2 : 1;             // accumulator width per issuer in units of Cout
+            p.n128 = L.n128;
             for (int ci = 0; ci < 5 && !found; ++ci) {
-                const int ns = env_ns ? env_ns : cand[ci][0], ks = env_ks ? env_ks : cand[ci][1];
-                if (ns * ks > kIssuersHalo || ns * ks * L.cout > 512 || ks > kk * kk) continue;
-                if (persist_mode == 2 && 2 * ns * ks * L.cout > 512) continue;     // only configurations that can double-buffer TMEM
+                const int ns = env_ns ? env_ns : cand[ci][0], ks = L.n128 ? 1 : (env_ks ? env_ks : cand[ci][1]);
+                if (ns * ks > kIssuersHalo || ns * ks * acw * L.cout > 512 || ks > kk * kk) continue;
+                // only configurations that can double-buffer TMEM (the n128 form may run with a single accumulator set)
+                if (persist_mode == 2 && !L.n128 && 2 * ns * ks * L.cout > 512) continue;
                 p.ns = ns; p.ks = ks;
                 p.halo_w = 8 * ns + halo_extra;
                 p.halo_rows = (16 + halo_extra) * p.halo_w;
@@ -893,7 +918,9 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
             }
             if (!found) return fail(DSU_E_INVALID, "halo convolution does not fit in shared memory: " + L.name);
             // persistent CTAs with double-buffered accumulators when two accumulator sets fit in TMEM
-            const bool persist = persist_mode != 0 && 2 * p.ns * p.ks * L.cout <= 512;
+            p.nsets = 2 * p.ns * p.ks * acw * L.cout <= 512 ? 2 : 1;
+            if (K.halo_nsets == 1) p.nsets = 1;
+            const bool persist = persist_mode != 0 && (p.nsets == 2 || L.n128);
             p.tps = 1;
             if (persist) {   // taps per weight stage: up to 3 while the ring stays >= 3 stages deep (per K-split group)
                 int tps = 3;
@@ -905,18 +932,18 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
                 p.sb = (p.sb / p.ks) * p.ks;
             }
             cols = 32;
-            while (cols < (persist ? 2 : 1) * p.ns * p.ks * L.cout) cols *= 2;
+            while (cols < p.nsets * p.ns * p.ks * acw * L.cout) cols *= 2;
             p.tmem_cols = cols;
             if (!persist) return fail(DSU_E_INVALID, "halo convolution: two accumulator sets do not fit in tensor memory: " + L.name);
             CUDA_TRY(launch_conv_halo_persist(p, st));
         } else {
             bool first = false;
-            if (L.first && first_mode != 0) {
+            if (L.first && (first_mode != 0 || E->exact)) {
                 // im2col-free persistent kernel: ring of pixel-linear halo tiles + the whole weight matrix in shared memory
                 p.ksize = L.k; p.pad = L.pad;
                 p.halo_w = 16;
                 p.halo_rows = 16 + L.k - 1;
-                p.halo_bytes = p.halo_rows * 16 * 16;
+                p.halo_bytes = p.halo_rows * 16 * 16 * (E->exact ? 2 : 1);      // split-fp16: hi plane, then lo plane
                 const int ks_max = std::min(4, std::min(L.k, 256 / L.cout));
                 p.ks = std::min(2, ks_max);
                 if (K.first_ks > 0) p.ks = std::max(1, std::min(ks_max, K.first_ks));
@@ -1068,6 +1095,8 @@ int dsu_set_knob(dsu_handle h, const char* name, int32_t value) {
         if (std::strcmp(kn.name, name) == 0) {
             if (kn.field == &Knobs::subpixel && h->knobs.subpixel != value)
                 return fail(DSU_E_STATE, "'subpixel' shapes the launch plan: set DSU_SUBPIXEL in the environment before dsu_create");
+            if (kn.field == &Knobs::n128 && h->knobs.n128 != value)
+                return fail(DSU_E_STATE, "'n128' shapes the weight packing: set DSU_N128 in the environment before dsu_create");
             h->knobs.*(kn.field) = value;
             return DSU_OK;
         }
