@@ -400,7 +400,9 @@ conv_ric_tm_kernel(const __grid_constant__ TmParams P) {
 #pragma unroll
                             for (int t = 0; t < 9; ++t) {
                                 tmem_st2(cb + t * 8, out[t].x, out[t].y);
+#ifndef DSU_TM_EXPERIMENT_SKIP_LO
                                 tmem_st2(cb + 72 + t * 8, out[t].z, out[t].w);
+#endif
                             }
                         }
                     }

@@ -920,7 +920,7 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
             // persistent CTAs with double-buffered accumulators when two accumulator sets fit in TMEM
             p.nsets = 2 * p.ns * p.ks * acw * L.cout <= 512 ? 2 : 1;
             if (K.halo_nsets == 1) p.nsets = 1;
-            const bool persist = persist_mode != 0 && (p.nsets == 2 || L.n128);
+            const bool persist = persist_mode != 0;      // the persistent kernel runs with one accumulator set when two do not fit
             p.tps = 1;
             if (persist) {   // taps per weight stage: up to 3 while the ring stays >= 3 stages deep (per K-split group)
                 int tps = 3;
@@ -934,7 +934,7 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
             cols = 32;
             while (cols < p.nsets * p.ns * p.ks * acw * L.cout) cols *= 2;
             p.tmem_cols = cols;
-            if (!persist) return fail(DSU_E_INVALID, "halo convolution: two accumulator sets do not fit in tensor memory: " + L.name);
+            if (!persist) return fail(DSU_E_INVALID, "halo convolution: the non-persistent kernel was removed (knob halo_persist = 0): " + L.name);
             CUDA_TRY(launch_conv_halo_persist(p, st));
         } else {
             bool first = false;

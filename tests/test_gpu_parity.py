@@ -197,6 +197,26 @@ def test_reference_on_gpu_agrees_with_cpu_oracle(dev):
         assert (y - ref).abs().max().item() < 2e-5
 
 
+@pytest.mark.parametrize("env", [{"DSU_N128": "0"}, {"DSU_N128": "1"}, {"DSU_FIRST": "0"}, {"DSU_N128": "1", "DSU_HALO_NSETS": "1"}])
+def test_split_fp16_stage2_plan_variants(dev, env, monkeypatch):
+    """Split-fp16 stage 2, plan-time variants (knobs read once at dsu_create): conv_11 / the smoothers with and without the
+    N = 128 issue form ([W_hi ; W_lo] no-swizzle weight tiles, 128-column accumulators summed by the epilogue, one or two
+    accumulator sets), conv0 in the im2col-free kernel with a lo plane or in tap mode.  All of them compute the same
+    three fp16 product sums, so they agree to fp32 accumulation order and all meet the parity tolerance."""
+    x = _frames_tensor(2, 72, 100, seed=29, stage=2)
+    m0, sd = _model(2, dev)
+    with torch.no_grad():
+        y0 = m0(x.to(dev)).cpu()
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    m1, _ = _model(2, dev)
+    with torch.no_grad():
+        y1 = m1(x.to(dev)).cpu()
+    ref = _oracle(2, sd, x)
+    assert (y1 - y0).abs().max().item() < 1e-4
+    assert (y0 - ref).abs().max().item() < TOL and (y1 - ref).abs().max().item() < TOL
+
+
 # ------------------------------------------------------------------ tensor-memory RIC kernel configurations
 def test_tensor_memory_kernel_issuer_and_stage_knobs(dev):
     """The tensor-memory RIC kernel with 1 / 3 issuing warps and the minimum weight ring gives the same result as the default

@@ -281,3 +281,31 @@ def test_subpixel_decomposition_of_upsample_conv_is_exact():
             xp = F.pad(x, (1 - px, px, 1 - py, py))
             got[:, :, py::2, px::2] = F.conv2d(xp, wc)
     assert torch.allclose(got, want, rtol=0, atol=1e-12)
+
+
+def test_n128_issue_form_of_the_split_fp16_product():
+    """Split-fp16 conv_11 (engine.cu compile_layer, ConvParams::n128): the weight tile of a (tap, 32-channel block) is a
+    no-swizzle K-major tile of 128 rows [W_hi ; W_lo] x 32 channels; a_hi x tile is one N = 128 MMA, a_lo x (first 64 rows) one
+    N = 64 MMA, and the epilogue adds columns c and 64 + c.  Restated with numpy: (1) the byte offset formula tiles the 8 KB
+    tile exactly once, (2) the two-MMA form equals a_hi.W_hi + a_lo.W_hi + a_hi.W_lo, (3) which is within 2^-20 relative of
+    the fp32 product (the lo x lo term is the only thing dropped)."""
+    rng = np.random.default_rng(7)
+    offs = set()
+    for row in range(128):
+        for c in range(32):
+            offs.add((row // 8) * 512 + (c // 8) * 128 + (row % 8) * 16 + (c % 8) * 2)
+    assert len(offs) == 128 * 32 and min(offs) == 0 and max(offs) == 8190 and all(o % 2 == 0 for o in offs)
+
+    a = rng.standard_normal((128, 32)).astype(np.float32) * 3
+    w = rng.standard_normal((64, 32)).astype(np.float32)
+    a_hi = a.astype(np.float16); a_lo = (a - a_hi.astype(np.float32)).astype(np.float16)
+    w_hi = w.astype(np.float16); w_lo = (w - w_hi.astype(np.float32)).astype(np.float16)
+    f = lambda t: t.astype(np.float64)
+    tile = np.concatenate([f(w_hi), f(w_lo)], axis=0)                  # 128 rows
+    d = f(a_hi) @ tile.T                                               # N = 128: [hi.W_hi | hi.W_lo]
+    d[:, :64] += f(a_lo) @ tile[:64].T                                 # N = 64 on the first 64 rows
+    got = d[:, :64] + d[:, 64:]                                        # epilogue: K-split sum, stride 64
+    three = f(a_hi) @ f(w_hi).T + f(a_lo) @ f(w_hi).T + f(a_hi) @ f(w_lo).T
+    assert np.allclose(got, three, rtol=0, atol=1e-12)
+    exact = f(a) @ f(w).T
+    assert np.abs(got - exact).max() < 2.0 ** -20 * np.abs(f(a)).max() * np.abs(f(w)).max() * 32
