@@ -166,11 +166,17 @@ class StylizeReport:
 def stylize_character(root_dir: str, uid: str, pipeline=None, *, device="cuda:0", precision: str = "fp16x3",
                       checkpoint_id: int = 99999, keep_stage1: bool = True, save_alpha: bool = True, gif: bool = False,
                       rank: int = 0, world: int = 1, workers: int = 8, batch: int = 16,
-                      pipeline_factory: Optional[Callable] = None) -> StylizeReport:
+                      pipeline_factory: Optional[Callable] = None, stack: Optional[bool] = None,
+                      write_png: Optional[bool] = None) -> StylizeReport:
     """``test_stage1.py --uid U`` + ``test_stage2.py --uid U`` (+ ``gif_writer.py``) in one pass over the character's
     ``mesh/blender_render`` tree.  ``pipeline`` is a ready :class:`StylizationPipeline` (weights already broadcast);
     otherwise the checkpoints are read from the tree.  ``pipeline_factory(sd1, sd2)`` exists for tests of the folder
-    logic without a GPU.  With ``world > 1`` the rank handles ``shard_range`` of every action's frames."""
+    logic without a GPU.  With ``world > 1`` the rank handles ``shard_range`` of every action's frames.
+
+    ``stack``: read the clip from its raw frame stacks (``frame_stack.py``: ``<action>/stack/{color,pos,edge}.npy``) instead of
+    decoding PNGs, and write the results as stacks too (None = use the stacks of every action that has them).  ``write_png``
+    forces / suppresses the reference's PNG result folders (default: PNGs for PNG inputs, stacks for stack inputs)."""
+    from . import frame_stack
     from .pipeline import shard_range
     data_root = os.path.join(root_dir, uid, "mesh", "blender_render")
     if pipeline is None:
@@ -183,12 +189,18 @@ def stylize_character(root_dir: str, uid: str, pipeline=None, *, device="cuda:0"
     rep = StylizeReport()
     for action in list_actions(data_root):
         adir = os.path.join(data_root, action)
-        names = list_frames(adir)
+        use_stack = frame_stack.has_stack(adir) if stack is None else bool(stack)
+        names = frame_stack.read_names(adir) if use_stack else list_frames(adir)
         lo, hi = shard_range(len(names), rank, world)
         if hi <= lo:
             continue
-        fs = FrameSet.load(adir, names[lo:hi], need_edge=True, workers=workers)
-        if fs.edge is None:
+        if use_stack:
+            t0 = time.perf_counter()
+            nm, c, p_, e = frame_stack.load_range(adir, lo, hi, need_edge=True)
+            fs = FrameSet(nm, c, p_, e, time.perf_counter() - t0)
+        else:
+            fs = FrameSet.load(adir, names[lo:hi], need_edge=True, workers=workers)
+        if fs.edge is None and not getattr(pipeline, "derive_edge", False):
             raise FileNotFoundError(adir + "/edge: stage 2 needs the edge maps (run_render.py:117-120)")
         rep.decode_s += fs.decode_seconds
         out = torch.empty_like(fs.color)
@@ -196,14 +208,22 @@ def stylize_character(root_dir: str, uid: str, pipeline=None, *, device="cuda:0"
         t0 = time.perf_counter()
         mid = pipeline.run_host(fs.color, fs.pos, fs.edge, out, keep_stage1=keep_stage1)
         rep.gpu_s += time.perf_counter() - t0
-        if keep_stage1:
-            rep.encode_s += save_frames(os.path.join(adir, STAGE1_RES), fs.names, mid, True, workers)
-        rep.encode_s += save_frames(os.path.join(adir, STAGE2_RES), fs.names, out, save_alpha, workers)
+        png = (not use_stack) if write_png is None else bool(write_png)
+        if use_stack:
+            t0 = time.perf_counter()
+            if keep_stage1:
+                frame_stack.save_range(adir, STAGE1_RES, mid, lo, len(names))
+            frame_stack.save_range(adir, STAGE2_RES, out, lo, len(names))
+            rep.encode_s += time.perf_counter() - t0
+        if png:
+            if keep_stage1:
+                rep.encode_s += save_frames(os.path.join(adir, STAGE1_RES), fs.names, mid, True, workers)
+            rep.encode_s += save_frames(os.path.join(adir, STAGE2_RES), fs.names, out, save_alpha, workers)
         rep.frames += len(fs)
         rep.actions[action] = len(fs)
     if gif and rank == 0 and world == 1:
         for action in rep.actions:          # gif_writer.py:13-21 (every action except the rest pose, stage-2 frames)
-            if action != "rest_pose":
+            if action != "rest_pose" and os.path.isdir(os.path.join(data_root, action, STAGE2_RES)):
                 write_gif(os.path.join(data_root, action, STAGE2_RES),
                           os.path.join(data_root, "..", "gif", action + "_" + STAGE2_RES + ".gif"))
     return rep
@@ -219,13 +239,29 @@ def main(argv=None) -> int:
     ap.add_argument("--no_stage1", action="store_true", help="do not write the intermediate res_stage1_mask_pos frames")
     ap.add_argument("--gif", action="store_true")
     ap.add_argument("--workers", type=int, default=8)
+    ap.add_argument("--pack", action="store_true", help="convert every action's PNG tree to raw frame stacks (stack/*.npy) and exit")
+    ap.add_argument("--stack", action="store_true", help="read / write raw frame stacks instead of PNGs (default: when present)")
+    ap.add_argument("--png", action="store_true", help="with stacks: also write the reference's PNG result folders")
+    ap.add_argument("--unpack", action="store_true", help="write the result stacks out as PNG folders and exit")
     a = ap.parse_args(argv)
+    if a.pack or a.unpack:
+        from . import frame_stack
+        data_root = os.path.join(a.root, a.uid, "mesh", "blender_render")
+        for action in list_actions(data_root):
+            adir = os.path.join(data_root, action)
+            if a.pack:
+                print("%s: packed %d frames" % (action, frame_stack.pack_action(adir, a.workers)))
+            else:
+                for layer in (STAGE1_RES, STAGE2_RES):
+                    if os.path.isfile(os.path.join(frame_stack.stack_dir(adir), layer + ".npy")):
+                        print("%s/%s: %d frames" % (action, layer, frame_stack.unpack_action(adir, layer, None, not a.no_alpha, a.workers)))
+        return 0
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     dev = "cuda:%d" % int(os.environ.get("LOCAL_RANK", "0"))
     rep = stylize_character(a.root, a.uid, device=dev, precision=a.precision, checkpoint_id=a.checkpoint_id,
                             keep_stage1=not a.no_stage1, save_alpha=not a.no_alpha, gif=a.gif, rank=rank, world=world,
-                            workers=a.workers)
-    print("rank %d: %d frames | PNG decode %.2f s | GPU (H2D + 2 stages + D2H) %.2f s = %.1f frames/s | PNG encode %.2f s"
+                            workers=a.workers, stack=True if a.stack else None, write_png=True if a.png else None)
+    print("rank %d: %d frames | decode / stack read %.2f s | GPU (H2D + 2 stages + D2H) %.2f s = %.1f frames/s | encode / stack write %.2f s"
           % (rank, rep.frames, rep.decode_s, rep.gpu_s, rep.gpu_fps, rep.encode_s), flush=True)
     return 0
 

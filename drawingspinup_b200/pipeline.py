@@ -75,6 +75,7 @@ class StylizationPipeline:
                  batch: int = 16, deterministic: bool = False, derive_edge: bool = False):
         self.device = torch.device(device)
         self.batch = int(batch)
+        self.derive_edge = bool(derive_edge) and sd_stage2 is not None
         a = dict(DEFAULT_ARGS if args is None else args)
         self.g1 = GeneratorJ_RIC(precision=precision, deterministic=deterministic, **a)
         self.g1.load_state_dict(sd_stage1)
