@@ -97,12 +97,15 @@ def _bn(rng, sd, prefix, c):
 def make_state_dict(stage: int, seed: int = 1234, filters: Sequence[int] = DEFAULT_FILTERS,
                     resnet_blocks: int = 7, input_channels: int = 6, tanh: bool = True,
                     append_smoothers: bool = True, use_bias: bool = False,
-                    out_gain: float = 1.0) -> "OrderedDict[str, np.ndarray]":
+                    out_gain: float = 1.0, norm: str = "batch_norm") -> "OrderedDict[str, np.ndarray]":
     """Seeded weights with the reference key order / shapes (models.py:24-111 stage 2,
     :200-291 stage 1).  BN running stats are non-trivial so that
     folding bugs cannot hide; ``conv_12`` is scaled by ``out_gain`` so the tanh output
-    uses its full range like a trained network."""
+    uses its full range like a trained network.  ``norm`` = 'instance_norm' / None: the twelve ``norm_layer`` modules have no
+    state (nn.InstanceNorm2d defaults, models.py:34-35); ``conv_11_a.2`` is a hard-coded BatchNorm2d either way (models.py:98)."""
     rng = np.random.default_rng(seed * 7919 + stage)
+    _bn_fixed = _bn
+    bn_l = (lambda *a: None) if norm != "batch_norm" else _bn_fixed
     f = list(filters)
     k0 = 3 if stage == 1 else 7
     sd: "OrderedDict[str, np.ndarray]" = OrderedDict()
@@ -112,19 +115,19 @@ def make_state_dict(stage: int, seed: int = 1234, filters: Sequence[int] = DEFAU
         if bias:
             sd[key + ".bias"] = rng.normal(0, 0.05, cout).astype(np.float32)
 
-    conv("conv0.conv", f[0], input_channels, k0); _bn(rng, sd, "conv0.normalization", f[0])
-    conv("conv1.conv", f[1], f[0], 3); _bn(rng, sd, "conv1.normalization", f[1])
-    conv("conv2.conv", f[2], f[1], 3); _bn(rng, sd, "conv2.normalization", f[2])
+    conv("conv0.conv", f[0], input_channels, k0); bn_l(rng, sd, "conv0.normalization", f[0])
+    conv("conv1.conv", f[1], f[0], 3); bn_l(rng, sd, "conv1.normalization", f[1])
+    conv("conv2.conv", f[2], f[1], 3); bn_l(rng, sd, "conv2.normalization", f[2])
     for i in range(resnet_blocks):
         p = "resnets.%d." % i
-        conv(p + "conv_0", f[2], f[2], 3); _bn(rng, sd, p + "normalization", f[2])
+        conv(p + "conv_0", f[2], f[2], 3); bn_l(rng, sd, p + "normalization", f[2])
         conv(p + "conv_1", f[2], f[2], 3)
         sd[p + "conv_1.weight"] *= np.float32(0.5)     # keep the residual stream from blowing up
-    conv("upconv2.1", f[4], f[3] + f[2], 3, bias=False); _bn(rng, sd, "upconv2.2", f[4])
-    conv("upconv1.1", f[4], f[4] + f[1], 3, bias=False); _bn(rng, sd, "upconv1.2", f[4])
+    conv("upconv2.1", f[4], f[3] + f[2], 3, bias=False); bn_l(rng, sd, "upconv2.2", f[4])
+    conv("upconv1.1", f[4], f[4] + f[1], 3, bias=False); bn_l(rng, sd, "upconv1.2", f[4])
     conv("conv_11.0", f[5], f[0] + f[4] + input_channels, k0)
     if append_smoothers:
-        conv("conv_11_a.0", f[5], f[5], 3); _bn(rng, sd, "conv_11_a.2", f[5])
+        conv("conv_11_a.0", f[5], f[5], 3); _bn_fixed(rng, sd, "conv_11_a.2", f[5])
         conv("conv_11_a.3", f[5], f[5], 3)
     k12 = "conv_12.0" if tanh else "conv_12"
     sd[k12 + ".weight"] = (_conv_w(rng, 3, f[5], 1) * np.float32(out_gain)).astype(np.float32)

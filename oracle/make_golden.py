@@ -59,6 +59,9 @@ def main():
     from PIL import Image
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)          # one summation order for the recorded vectors
+    if os.environ.get("GOLDEN_ONLY", "") == "norm":      # add the norm-variant vectors without rewriting the older files
+        real_save = np.savez_compressed
+        np.savez_compressed = lambda path, **kw: real_save(path, **kw) if ("_norm_" in path) else None
     h, w, b = 32, 40, 2
     color, pos, edge = synth.make_frames(b, h, w, seed=101)
 
@@ -101,6 +104,24 @@ def main():
         with torch.no_grad():
             y = _no_cuda(m, xv)
         np.savez_compressed(os.path.join(OUT, "generator_variant_stage%d.npz" % stage), x=xv.numpy(), y=y.numpy())
+
+    # ---- norm_layer='instance_norm' (models.py:34-35) and norm_layer=None, default widths, 2 residual blocks
+    if os.environ.get("GOLDEN_ONLY", "") in ("", "norm"):
+        xn = torch.from_numpy(pre2[:, :, :24, :32].copy())
+        for norm in ("instance_norm", None):
+            nv = dict(ARGS, resnet_blocks=2, norm_layer=norm)
+            for stage, cls in ((1, rm.GeneratorJ_RIC), (2, rm.GeneratorJ)):
+                if norm is None and stage == 1:
+                    continue        # the reference's stage-1 forward indexes self.conv0[2] (models.py:303): IndexError without a norm module
+                sd_np = synth.make_state_dict(stage, seed=91, resnet_blocks=2, out_gain=0.25, norm=norm or "none")
+                m = cls(**nv).eval()
+                m.load_state_dict(synth.to_torch_state_dict(sd_np))
+                with torch.no_grad():
+                    y = _no_cuda(m, xn)
+                np.savez_compressed(os.path.join(OUT, "generator_%s_stage%d.npz" % (norm or "no_norm", stage)), x=xn.numpy(), y=y.numpy())
+                print(norm, "stage", stage, "y range", float(y.min()), float(y.max()))
+    if os.environ.get("GOLDEN_ONLY", "") == "norm":
+        return
 
     # ---- RIC coordinates
     coords = _no_cuda(rm.generate_coordinates, 2, 24, 20)

@@ -131,9 +131,15 @@ def _deform(x, offsets, weight, use_torchvision):
 # ----------------------------------------------------------------------------
 # building blocks shared by both generators
 # ----------------------------------------------------------------------------
-def _bn(x, sd, prefix):
+def _bn(x, sd, prefix, cfg=None):
     """Eval-mode BatchNorm2d = per-channel affine from running stats (scripts call
-    generator.eval(): test_stage1.py:48, test_stage2.py:55)."""
+    generator.eval(): test_stage1.py:48, test_stage2.py:55).  A ``norm_layer`` module without state is either absent
+    (norm_layer=None) or nn.InstanceNorm2d with its defaults (models.py:34-35: affine=False, track_running_stats=False,
+    eps=1e-5 -> per-(frame, channel) statistics over H x W, biased variance, in eval mode too)."""
+    if prefix + ".weight" not in sd:
+        if cfg is not None and cfg.get("norm") == "instance_norm":
+            return F.instance_norm(x, eps=BN_EPS)
+        return x
     g, b = sd[prefix + ".weight"], sd[prefix + ".bias"]
     m, v = sd[prefix + ".running_mean"], sd[prefix + ".running_var"]
     inv = torch.rsqrt(v + BN_EPS)
@@ -159,26 +165,26 @@ def generator_j_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, cfg: Optio
     cfg = cfg or default_config(2)
     rec = (lambda k, v: taps.__setitem__(k, v.clone())) if taps is not None else (lambda k, v: None)
     o0 = F.leaky_relu(_bn(F.conv2d(x, sd["conv0.conv.weight"], _bias(sd, "conv0.conv.bias"), 1, 3),
-                          sd, "conv0.normalization"), 0.2)
+                          sd, "conv0.normalization", cfg), 0.2)
     rec("conv0", o0)
     o1 = F.leaky_relu(_bn(F.conv2d(o0, sd["conv1.conv.weight"], _bias(sd, "conv1.conv.bias"), 2, 1),
-                          sd, "conv1.normalization"), 0.2)
+                          sd, "conv1.normalization", cfg), 0.2)
     rec("conv1", o1)
     o2 = F.leaky_relu(_bn(F.conv2d(o1, sd["conv2.conv.weight"], _bias(sd, "conv2.conv.bias"), 2, 1),
-                          sd, "conv2.normalization"), 0.2)
+                          sd, "conv2.normalization", cfg), 0.2)
     rec("conv2", o2)
     out = o2
     for i in range(cfg["resnet_blocks"]):
         p = "resnets.%d." % i
         t = F.conv2d(F.relu(out), sd[p + "conv_0.weight"], _bias(sd, p + "conv_0.bias"), 1, 1)
-        t = F.relu(_bn(t, sd, p + "normalization"))
+        t = F.relu(_bn(t, sd, p + "normalization", cfg))
         out = F.conv2d(t, sd[p + "conv_1.weight"], _bias(sd, p + "conv_1.bias"), 1, 1) + out
         rec("res%d" % i, out)
     t = F.interpolate(torch.cat((out, o2), 1), scale_factor=2, mode="nearest")
-    out = F.relu(_bn(F.conv2d(t, sd["upconv2.1.weight"], None, 1, 1), sd, "upconv2.2"))
+    out = F.relu(_bn(F.conv2d(t, sd["upconv2.1.weight"], None, 1, 1), sd, "upconv2.2", cfg))
     rec("upconv2", out)
     t = F.interpolate(torch.cat((out, o1), 1), scale_factor=2, mode="nearest")
-    out = F.relu(_bn(F.conv2d(t, sd["upconv1.1.weight"], None, 1, 1), sd, "upconv1.2"))
+    out = F.relu(_bn(F.conv2d(t, sd["upconv1.1.weight"], None, 1, 1), sd, "upconv1.2", cfg))
     rec("upconv1", out)
     out = F.relu(F.conv2d(torch.cat((out, o0, x), 1), sd["conv_11.0.weight"], _bias(sd, "conv_11.0.bias"), 1, 3))
     rec("conv_11", out)
@@ -210,23 +216,23 @@ def generator_j_ric_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, cfg: O
     c1 = ric_offsets(int(h / 2), int(w / 2)).to(x.device)
     c2 = ric_offsets(int(h / 4), int(w / 4)).to(x.device)
     dc = lambda a, off, key: _deform(a, off, sd[key], use_torchvision)
-    o0 = F.leaky_relu(_bn(dc(x, c0, "conv0.conv.weight"), sd, "conv0.normalization"), 0.2)
+    o0 = F.leaky_relu(_bn(dc(x, c0, "conv0.conv.weight"), sd, "conv0.normalization", cfg), 0.2)
     rec("conv0", o0)
-    o1 = F.leaky_relu(_bn(dc(F.max_pool2d(o0, 2, 2), c1, "conv1.conv.weight"), sd, "conv1.normalization"), 0.2)
+    o1 = F.leaky_relu(_bn(dc(F.max_pool2d(o0, 2, 2), c1, "conv1.conv.weight"), sd, "conv1.normalization", cfg), 0.2)
     rec("conv1", o1)
-    o2 = F.leaky_relu(_bn(dc(F.max_pool2d(o1, 2, 2), c2, "conv2.conv.weight"), sd, "conv2.normalization"), 0.2)
+    o2 = F.leaky_relu(_bn(dc(F.max_pool2d(o1, 2, 2), c2, "conv2.conv.weight"), sd, "conv2.normalization", cfg), 0.2)
     rec("conv2", o2)
     out = o2
     for i in range(cfg["resnet_blocks"]):
         p = "resnets.%d." % i
-        t = F.relu(_bn(dc(F.relu(out), c2, p + "conv_0.weight"), sd, p + "normalization"))
+        t = F.relu(_bn(dc(F.relu(out), c2, p + "conv_0.weight"), sd, p + "normalization", cfg))
         out = dc(t, c2, p + "conv_1.weight") + out
         rec("res%d" % i, out)
     t = F.interpolate(torch.cat((out, o2), 1), scale_factor=2, mode="nearest")
-    out = F.relu(_bn(dc(t, c1, "upconv2.1.weight"), sd, "upconv2.2"))
+    out = F.relu(_bn(dc(t, c1, "upconv2.1.weight"), sd, "upconv2.2", cfg))
     rec("upconv2", out)
     t = F.interpolate(torch.cat((out, o1), 1), scale_factor=2, mode="nearest")
-    out = F.relu(_bn(dc(t, c0, "upconv1.1.weight"), sd, "upconv1.2"))
+    out = F.relu(_bn(dc(t, c0, "upconv1.1.weight"), sd, "upconv1.2", cfg))
     rec("upconv1", out)
     out = F.relu(dc(torch.cat((out, o0, x), 1), c0, "conv_11.0.weight"))
     rec("conv_11", out)

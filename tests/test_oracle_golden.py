@@ -41,6 +41,21 @@ def test_generator_variant_config_matches_reference_golden(golden_dir, stage):
     assert np.abs(y.numpy() - g["y"]).max() < 2e-4
 
 
+@pytest.mark.parametrize("norm,stage", [("instance_norm", 1), ("instance_norm", 2), (None, 2)])
+def test_generator_norm_layer_variants_match_reference_golden(golden_dir, norm, stage):
+    """norm_layer='instance_norm' (nn.InstanceNorm2d defaults: per-(frame, channel) statistics, no state) and norm_layer=None
+    (models.py:29-35), recorded from the live reference.  (norm_layer=None is not runnable for stage 1 in the reference
+    itself: its forward indexes self.conv0[2], models.py:303.)"""
+    g = _load(golden_dir, "generator_%s_stage%d.npz" % (norm or "no_norm", stage))
+    sd = synth.to_torch_state_dict(synth.make_state_dict(stage, seed=91, resnet_blocks=2, out_gain=0.25, norm=norm or "none"))
+    assert not any("normalization" in k or k.startswith("upconv2.2") for k in sd) and "conv_11_a.2.weight" in sd
+    cfg = dict(rp.default_config(stage), resnet_blocks=2, norm=norm)
+    x = torch.from_numpy(g["x"])
+    with torch.no_grad():
+        y = rp.generator_j_ric_forward(sd, x, cfg) if stage == 1 else rp.generator_j_forward(sd, x, cfg)
+    assert np.abs(y.numpy() - g["y"]).max() < 2e-4
+
+
 def test_ric_port_equals_torchvision_path():
     sd = synth.to_torch_state_dict(synth.make_state_dict(1, seed=3, out_gain=0.25))
     x = torch.from_numpy(np.random.default_rng(0).standard_normal((1, 6, 16, 24)).astype(np.float32))
