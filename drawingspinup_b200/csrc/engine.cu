@@ -55,6 +55,7 @@ struct LayerDef {
     int act = 0;
     int out_buf = -1, out_choff = 0, out_relu = 0, out2_buf = -1;
     int resid_in = 0, resid_out = 0, final = 0;
+    int inorm = 0;         // norm_layer='instance_norm': the epilogue leaves the raw fp32 output in a scratch buffer; a type-2 step normalises
     int halo = 0;          // plain stride-1 conv run by the halo-reuse kernel (conv_halo_persist.cu)
     int b_bytes = 0;       // bytes of one chunk's weight tile(s) (0 = Cout x 128)
     int n128 = 0;          // split-fp16 Cout = 64 halo layer packed for the N = 128 issue form (ConvParams::n128)
@@ -82,7 +83,7 @@ struct LayerDef {
 };
 
 struct Step {
-    int type;    // 0 conv, 1 maxpool
+    int type;    // 0 conv, 1 maxpool, 2 instance norm + activation + stores of layer `layer` (after its last launch)
     int layer;
     int src, src_choff, C, dst;
 };
@@ -169,6 +170,10 @@ struct dsu_engine {
     size_t buf_cap[NBUF]{};
     float* resid = nullptr;
     size_t resid_cap = 0;
+    float* inorm_x = nullptr;      // norm_layer='instance_norm': raw fp32 output of the convolution being normalised
+    float2* inorm_stats = nullptr; // [B][Cmax] (mean, 1/sqrt(var + eps))
+    double* inorm_acc = nullptr;   // [B][Cmax][2] sum, sum of squares
+    size_t inorm_cap = 0, inorm_stats_cap = 0;
     Level lv[3];
     std::map<std::pair<int, int>, std::vector<float>> user_offsets;
     uint8_t *io_color = nullptr, *io_pos = nullptr, *io_edge = nullptr, *io_out = nullptr;
@@ -198,6 +203,7 @@ int build_plan(dsu_engine* E) {
     const int* f = c.filters;
     const bool ric = c.kind == DSU_KIND_GENERATORJ_RIC;
     const bool bn = c.norm == DSU_NORM_BATCH;
+    const bool inorm = c.norm == DSU_NORM_INSTANCE;     // the twelve norm_layer modules are nn.InstanceNorm2d (no state)
     const int cin = c.input_channels, cp = E->cin_pad;
     const int k0 = ric ? 3 : 7;
     auto conv_keys = [&](const std::string& p, int co, int ci, int k, bool may_bias) {
@@ -245,18 +251,19 @@ int build_plan(dsu_engine* E) {
     // in stage 1 the deformable calls pass only .weight, so conv biases are never applied (models.py:302-351)
     auto bias_of = [&](const std::string& p) { return (c.use_bias && !ric) ? p + ".bias" : std::string(); };
     auto add = [&](LayerDef L) { E->layers.push_back(L); E->steps.push_back(Step{0, (int)E->layers.size() - 1, 0, 0, 0, 0}); };
+    auto add_norm = [&]() { if (inorm) E->steps.push_back(Step{2, (int)E->layers.size() - 1, 0, 0, 0, 0}); };
     {
         LayerDef L; L.name = "conv0"; L.wkey = "conv0.conv.weight"; L.bkey = bias_of("conv0.conv");
         L.bn = bn ? "conv0.normalization" : ""; L.k = k0; L.pad = k0 / 2; L.ric = ric; L.cout = f[0]; L.level_out = 0;
-        L.segs = {{SK0, f[0], cp, 0, cin}}; L.act = 2; L.out_buf = SK0; L.out_choff = 0;
-        add(L);
+        L.segs = {{SK0, f[0], cp, 0, cin}}; L.act = 2; L.out_buf = SK0; L.out_choff = 0; L.inorm = inorm;
+        add(L); add_norm();
     }
     if (ric) E->steps.push_back(Step{1, -1, SK0, 0, f[0], P0});
     {
         LayerDef L; L.name = "conv1"; L.wkey = "conv1.conv.weight"; L.bkey = bias_of("conv1.conv");
         L.bn = bn ? "conv1.normalization" : ""; L.stride = ric ? 1 : 2; L.ric = ric; L.cout = f[1]; L.level_out = 1;
-        L.segs = {{ric ? P0 : SK0, 0, f[0], 0, f[0]}}; L.act = 2; L.out_buf = O1;
-        add(L);
+        L.segs = {{ric ? P0 : SK0, 0, f[0], 0, f[0]}}; L.act = 2; L.out_buf = O1; L.inorm = inorm;
+        add(L); add_norm();
     }
     if (ric) E->steps.push_back(Step{1, -1, O1, 0, f[1], P1});
     const bool has_res = c.resnet_blocks > 0;
@@ -266,14 +273,15 @@ int build_plan(dsu_engine* E) {
         L.segs = {{ric ? P1 : O1, 0, f[1], 0, f[1]}}; L.act = 2;
         if (has_res) { L.out_buf = TT; L.out_relu = 1; L.out2_buf = O2; L.resid_out = 1; }
         else L.out_buf = O2;
-        add(L);
+        L.inorm = inorm;
+        add(L); add_norm();
     }
     for (int i = 0; i < c.resnet_blocks; ++i) {
         const std::string p = "resnets." + std::to_string(i) + ".";
         LayerDef A; A.name = p + "conv_0"; A.wkey = p + "conv_0.weight"; A.bkey = bias_of(p + "conv_0");
         A.bn = bn ? p + "normalization" : ""; A.ric = ric; A.cout = f[2]; A.level_out = 2;
-        A.segs = {{TT, 0, f[2], 0, f[2]}}; A.act = 1; A.out_buf = UU;
-        add(A);
+        A.segs = {{TT, 0, f[2], 0, f[2]}}; A.act = 1; A.out_buf = UU; A.inorm = inorm;
+        add(A); add_norm();
         LayerDef Bl; Bl.name = p + "conv_1"; Bl.wkey = p + "conv_1.weight"; Bl.bkey = bias_of(p + "conv_1");
         Bl.ric = ric; Bl.cout = f[2]; Bl.level_out = 2;
         Bl.segs = {{UU, 0, f[2], 0, f[2]}}; Bl.act = 0; Bl.resid_in = 1; Bl.resid_out = 1;
@@ -284,7 +292,8 @@ int build_plan(dsu_engine* E) {
     // MACs; validated on hardware in round 2, profiles/r02a_experimental.log); DSU_SUBPIXEL=0 at dsu_create restores the 3x3 form
     const bool subpixel = !ric && E->knobs.subpixel != 0;
     auto add_up = [&](LayerDef L) {
-        if (!subpixel) { L.up = 1; add(L); return; }
+        L.inorm = inorm;
+        if (!subpixel) { L.up = 1; add(L); add_norm(); return; }
         const std::string base = L.name;
         for (int cls = 0; cls < 4; ++cls) {
             LayerDef S = L;
@@ -292,6 +301,7 @@ int build_plan(dsu_engine* E) {
             S.up = 0; S.sub = cls; S.wk = 3; S.k = 2; S.pad = 0;
             add(S);
         }
+        add_norm();          // statistics over the whole output: after the fourth class
     };
     {
         LayerDef L; L.name = "upconv2"; L.wkey = "upconv2.1.weight"; L.bn = bn ? "upconv2.2" : "";
@@ -759,6 +769,29 @@ int ensure_shape(dsu_engine* E, int B, int H, int W) {
         CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&E->resid), rbytes));
         E->resid_cap = rbytes;
     }
+    if (E->cfg.norm == DSU_NORM_INSTANCE) {
+        size_t need = 0; int cmax = 0;
+        for (const LayerDef& L : E->layers)
+            if (L.inorm) {
+                need = std::max(need, static_cast<size_t>(B) * (H >> L.level_out) * (W >> L.level_out) * L.cout * sizeof(float));
+                cmax = std::max(cmax, L.cout);
+            }
+        if (need > E->inorm_cap) {
+            if (E->inorm_x) cudaFree(E->inorm_x);
+            E->inorm_x = nullptr;
+            CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&E->inorm_x), need));
+            E->inorm_cap = need;
+        }
+        const size_t sneed = static_cast<size_t>(B) * cmax;
+        if (sneed > E->inorm_stats_cap) {
+            if (E->inorm_stats) cudaFree(E->inorm_stats);
+            if (E->inorm_acc) cudaFree(E->inorm_acc);
+            E->inorm_stats = nullptr; E->inorm_acc = nullptr;
+            CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&E->inorm_stats), sneed * sizeof(float2)));
+            CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&E->inorm_acc), sneed * 2 * sizeof(double)));
+            E->inorm_stats_cap = sneed;
+        }
+    }
     if (E->cfg.kind == DSU_KIND_GENERATORJ_RIC)
         for (int l = 0; l < 3; ++l) {
             int rc = build_level(E, E->lv[l], H >> l, W >> l);
@@ -802,6 +835,25 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
             continue;
         }
         const LayerDef& L = E->layers[sp.layer];
+        if (sp.type == 2) {
+            // nn.InstanceNorm2d + activation + the stores of layer L's epilogue, from the raw output its launch(es) left in inorm_x
+            InstNormApply a{};
+            a.x = E->inorm_x; a.stats = E->inorm_stats;
+            a.B = B; a.HW = (H >> L.level_out) * (W >> L.level_out); a.C = L.cout; a.act = L.act;
+            a.resid = L.resid_out ? E->resid : nullptr;
+            if (L.out_buf >= 0) {
+                a.out_pitch = E->buf_C[L.out_buf]; a.out_choff = L.out_choff; a.out_relu = L.out_relu;
+                if (E->f32_acts) a.out_f32 = reinterpret_cast<float*>(E->buf_hi[L.out_buf]);
+                else { a.out_hi = E->buf_hi[L.out_buf]; a.out_lo = E->buf_lo[L.out_buf]; }
+            }
+            if (L.out2_buf >= 0) {
+                a.out2_pitch = E->buf_C[L.out2_buf]; a.out2_choff = 0;
+                if (E->f32_acts) a.out2_f32 = reinterpret_cast<float*>(E->buf_hi[L.out2_buf]);
+                else { a.out2_hi = E->buf_hi[L.out2_buf]; a.out2_lo = E->buf_lo[L.out2_buf]; }
+            }
+            CUDA_TRY(instance_norm(a, E->inorm_acc, st));
+            continue;
+        }
         ConvParams p{};
         // a sub-pixel class iterates over the low-resolution grid (one level below its output buffer)
         const int grid_level = L.level_out + (L.sub >= 0 ? 1 : 0);
@@ -838,6 +890,11 @@ int run_network(dsu_engine* E, int B, int H, int W, float* y_dev, uint8_t* y_rgb
             e.out2_hi = E->buf_hi[L.out2_buf]; e.out2_lo = E->buf_lo[L.out2_buf];
             e.out2_pitch = E->buf_C[L.out2_buf]; e.out2_choff = 0;
             if (E->f32_acts) { e.out2_f32 = reinterpret_cast<float*>(E->buf_hi[L.out2_buf]); e.out2_hi = nullptr; e.out2_lo = nullptr; }
+        }
+        if (L.inorm) {
+            // raw convolution output (+ bias) -> fp32 scratch through the residual-stream store; everything else happens in the type-2 step
+            e.act = 0; e.resid_in = 0; e.resid_out = 1; e.resid = E->inorm_x; e.out_relu = 0;
+            e.out_hi = e.out_lo = e.out2_hi = e.out2_lo = nullptr; e.out_f32 = e.out2_f32 = nullptr;
         }
         if (L.final) {
             e.w12 = E->d_w12; e.b12 = E->d_b12; e.tanh_flag = E->cfg.tanh;
@@ -990,9 +1047,7 @@ int dsu_create(const dsu_config* cfg, dsu_handle* out) {
     *out = nullptr;
     if (cfg->kind != DSU_KIND_GENERATORJ_RIC && cfg->kind != DSU_KIND_GENERATORJ)
         return fail(DSU_E_INVALID, "kind must be DSU_KIND_GENERATORJ_RIC or DSU_KIND_GENERATORJ");
-    if (cfg->norm == DSU_NORM_INSTANCE)
-        return fail(DSU_E_NOTIMPL, "norm_layer='instance_norm' (models.py:34-35) is not implemented; no shipped config uses it");
-    if (cfg->norm != DSU_NORM_BATCH && cfg->norm != DSU_NORM_NONE) return fail(DSU_E_INVALID, "bad norm");
+    if (cfg->norm != DSU_NORM_BATCH && cfg->norm != DSU_NORM_NONE && cfg->norm != DSU_NORM_INSTANCE) return fail(DSU_E_INVALID, "bad norm");
     if (cfg->precision != DSU_PREC_FP16 && cfg->precision != DSU_PREC_FP16X3) return fail(DSU_E_INVALID, "bad precision");
     if (cfg->input_channels < 1 || cfg->input_channels > 16) return fail(DSU_E_INVALID, "input_channels must be in [1,16]");
     if (cfg->resnet_blocks < 0 || cfg->resnet_blocks > 64) return fail(DSU_E_INVALID, "resnet_blocks out of range");
@@ -1038,6 +1093,7 @@ void dsu_destroy(dsu_handle h) {
     for (int b = 0; b < NBUF; ++b) { cudaFree(h->buf_hi[b]); cudaFree(h->buf_lo[b]); }
     for (int l = 0; l < 3; ++l) { cudaFree(h->lv[l].lyx); cudaFree(h->lv[l].oct); cudaFree(h->lv[l].wh); }
     cudaFree(h->resid); cudaFree(h->d_w12); cudaFree(h->d_b12);
+    cudaFree(h->inorm_x); cudaFree(h->inorm_stats); cudaFree(h->inorm_acc);
     if (h->wd_host) cudaFreeHost(h->wd_host);
     cudaFree(h->io_color); cudaFree(h->io_pos); cudaFree(h->io_edge); cudaFree(h->io_out);
     delete h;
@@ -1172,6 +1228,12 @@ size_t dsu_workspace_bytes(dsu_handle h, int32_t B, int32_t H, int32_t W) {
         if (h->buf_used[b])
             total += static_cast<size_t>(B) * (H >> h->buf_level[b]) * (W >> h->buf_level[b]) * h->buf_C[b] * 2 * (h->exact ? 2 : 1);
     if (h->cfg.resnet_blocks > 0) total += static_cast<size_t>(B) * (H >> 2) * (W >> 2) * h->cfg.filters[2] * 4;
+    if (h->cfg.norm == DSU_NORM_INSTANCE) {
+        size_t need = 0;
+        for (const LayerDef& L : h->layers)
+            if (L.inorm) need = std::max(need, static_cast<size_t>(B) * (H >> L.level_out) * (W >> L.level_out) * L.cout * 4);
+        total += need;
+    }
     if (h->cfg.kind == DSU_KIND_GENERATORJ_RIC)
         for (int l = 0; l < 3; ++l) total += static_cast<size_t>(H >> l) * (W >> l) * 65;
     return total;
@@ -1179,7 +1241,10 @@ size_t dsu_workspace_bytes(dsu_handle h, int32_t B, int32_t H, int32_t W) {
 
 int dsu_forward_launches(dsu_handle h, int32_t B, int32_t H, int32_t W) {
     (void)B; (void)H; (void)W;
-    return h ? static_cast<int>(h->steps.size()) + 1 : 0;
+    if (!h) return 0;
+    int n = 1;                                      // ingest
+    for (const Step& sp : h->steps) n += sp.type == 2 ? 3 : 1;     // instance norm = statistics + finish + apply
+    return n;
 }
 
 double dsu_forward_flops(dsu_handle h, int32_t B, int32_t H, int32_t W) {
@@ -1242,7 +1307,7 @@ int dsu_profile_forward(dsu_handle h, int32_t B, int32_t H, int32_t W, int32_t r
 const char* dsu_step_name(dsu_handle h, int32_t index) {
     if (!h || index < 0 || index >= static_cast<int>(h->steps.size())) return "";
     const Step& sp = h->steps[index];
-    return sp.type == 0 ? h->layers[sp.layer].name.c_str() : "maxpool";
+    return sp.type == 0 ? h->layers[sp.layer].name.c_str() : sp.type == 1 ? "maxpool" : "instance_norm";
 }
 
 int dsu_frames_to_tensor(const uint8_t* color_dev, const uint8_t* pos_dev, const uint8_t* edge_dev,

@@ -226,6 +226,75 @@ __global__ void ingest_u8_kernel(const uchar4* __restrict__ color, const uchar4*
 }
 
 
+// ---- nn.InstanceNorm2d (norm_layer='instance_norm', models.py:34-35; defaults: affine=False, no running stats, eps 1e-5,
+// biased variance) between a convolution and its activation.  The convolution's epilogue leaves its raw fp32 output
+// x[B][HW][C] in a scratch buffer; (1) per-(frame, channel) sum and sum of squares, accumulated in fp64 (slices of the
+// frame per block, one atomicAdd per (block, channel)); (2) mean / 1/sqrt(var + eps); (3) normalise, activation, and the
+// stores the fused epilogue would have done (residual stream, un-ReLU'd second copy, fp16 hi[/lo] or fp32 NHWC output).
+__global__ void instnorm_stats_kernel(const float* __restrict__ x, int HW, int C, int rows_per_slice, double* acc) {
+    __shared__ double s_sum[8][33], s_sq[8][33];
+    const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;              // 8 pixel rows x 32 channels per block step
+    const int c = blockIdx.x * 32 + lane, n = blockIdx.z;
+    const int p0 = blockIdx.y * rows_per_slice, p1 = min(HW, p0 + rows_per_slice);
+    double s = 0.0, q = 0.0;
+    if (c < C) {
+        const float* base = x + static_cast<size_t>(n) * HW * C + c;
+        for (int p = p0 + row; p < p1; p += 8) {
+            const double v = static_cast<double>(base[static_cast<size_t>(p) * C]);
+            s += v; q += v * v;
+        }
+    }
+    s_sum[row][lane] = s; s_sq[row][lane] = q;
+    __syncthreads();
+    if (row == 0 && c < C) {
+#pragma unroll
+        for (int r = 1; r < 8; ++r) { s += s_sum[r][lane]; q += s_sq[r][lane]; }
+        atomicAdd(acc + (static_cast<size_t>(n) * C + c) * 2, s);
+        atomicAdd(acc + (static_cast<size_t>(n) * C + c) * 2 + 1, q);
+    }
+}
+
+__global__ void instnorm_finish_kernel(const double* __restrict__ acc, int total, int HW, float2* stats) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const double mean = acc[2 * i] / HW;
+    double var = acc[2 * i + 1] / HW - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    stats[i] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + 1e-5)));
+}
+
+__global__ void instnorm_apply_kernel(InstNormApply a) {
+    const int G = a.C / 8;
+    const size_t total = static_cast<size_t>(a.B) * a.HW * G;
+    const size_t t = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (t >= total) return;
+    const int g = static_cast<int>(t % G);
+    const size_t pix = t / G;
+    const int n = static_cast<int>(pix / a.HW);
+    const float* src = a.x + pix * a.C + g * 8;
+    const float4 x0 = reinterpret_cast<const float4*>(src)[0], x1 = reinterpret_cast<const float4*>(src)[1];
+    float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    const float2* st = a.stats + static_cast<size_t>(n) * a.C + g * 8;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float2 ms = st[c];
+        v[c] = (v[c] - ms.x) * ms.y;
+        if (a.act == 1) v[c] = fmaxf(v[c], 0.0f);
+        else if (a.act == 2) v[c] = fmaxf(v[c], 0.2f * v[c]);
+    }
+    if (a.resid) store8_f32(a.resid + pix * a.C + g * 8, v);
+    if (a.out2_f32) store8_f32(a.out2_f32 + pix * a.out2_pitch + a.out2_choff + g * 8, v);
+    else if (a.out2_hi) store8(a.out2_hi + pix * a.out2_pitch + a.out2_choff + g * 8,
+                               a.out2_lo ? a.out2_lo + pix * a.out2_pitch + a.out2_choff + g * 8 : nullptr, v);
+    if (a.out_relu) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = fmaxf(v[c], 0.0f);
+    }
+    if (a.out_f32) store8_f32(a.out_f32 + pix * a.out_pitch + a.out_choff + g * 8, v);
+    else if (a.out_hi) store8(a.out_hi + pix * a.out_pitch + a.out_choff + g * 8,
+                              a.out_lo ? a.out_lo + pix * a.out_pitch + a.out_choff + g * 8 : nullptr, v);
+}
+
 inline unsigned blocks_for(size_t n, int threads) { return static_cast<unsigned>((n + threads - 1) / threads); }
 
 }  // namespace
@@ -278,6 +347,20 @@ cudaError_t compose_rgba(const float* y, const float* mask, int B, int H, int W,
 cudaError_t pos2edge(const uint8_t* pos, int B, int H, int W, uint8_t* edge, cudaStream_t st) {
     const size_t np = static_cast<size_t>(H) * W * B;
     pos2edge_kernel<<<blocks_for(np, 256), 256, 0, st>>>(reinterpret_cast<const uchar4*>(pos), B, H, W, edge);
+    return cudaGetLastError();
+}
+
+cudaError_t instance_norm(const InstNormApply& a, double* acc, cudaStream_t st) {
+    if (a.C % 8 || a.B < 1 || a.HW < 1 || !a.x || !a.stats || !acc) return cudaErrorInvalidValue;
+    cudaError_t e = cudaMemsetAsync(acc, 0, static_cast<size_t>(a.B) * a.C * 2 * sizeof(double), st);
+    if (e != cudaSuccess) return e;
+    int slices = (a.HW + 4095) / 4096;                       // >= 4096 pixels per block and channel group, at most 64 slices
+    slices = slices > 64 ? 64 : slices;
+    const int rows = (a.HW + slices - 1) / slices;
+    instnorm_stats_kernel<<<dim3((a.C + 31) / 32, slices, a.B), 256, 0, st>>>(a.x, a.HW, a.C, rows, acc);
+    instnorm_finish_kernel<<<blocks_for(static_cast<size_t>(a.B) * a.C, 128), 128, 0, st>>>(acc, a.B * a.C, a.HW, a.stats);
+    const size_t total = static_cast<size_t>(a.B) * a.HW * (a.C / 8);
+    instnorm_apply_kernel<<<blocks_for(total, 256), 256, 0, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -23,4 +23,21 @@ cudaError_t overlap_edge(const uint8_t* edge, uint8_t* rgba, size_t npix, cudaSt
 cudaError_t compose_rgba(const float* y, const float* mask, int B, int H, int W, uint8_t* out, cudaStream_t st);
 cudaError_t pos2edge(const uint8_t* pos, int B, int H, int W, uint8_t* edge, cudaStream_t st);
 
+// nn.InstanceNorm2d between a convolution (raw fp32 output x[B][HW][C] left by its epilogue) and its activation, followed by
+// the stores the fused epilogue would have done.  Three small launches: statistics (fp64 accumulation), finish, apply.
+struct InstNormApply {
+    const float* x;          // raw convolution output, fp32 NHWC, pitch C
+    float2* stats;           // [B][C] (mean, 1/sqrt(var + eps)) - written by the call
+    int B, HW, C;
+    int act;                 // 0 none, 1 ReLU, 2 LeakyReLU(0.2), applied after the normalisation
+    float* resid;            // fp32 residual stream [pix][C] to write, or null
+    __half *out_hi, *out_lo; // main output (fp16 hi[/lo]) or out_f32; optional ReLU first
+    float* out_f32;
+    int out_pitch, out_choff, out_relu;
+    __half *out2_hi, *out2_lo;   // second copy taken before out_relu, or null
+    float* out2_f32;
+    int out2_pitch, out2_choff;
+};
+cudaError_t instance_norm(const InstNormApply& a, double* acc /* [B][C][2] scratch */, cudaStream_t st);
+
 }  // namespace dsu

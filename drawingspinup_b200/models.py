@@ -96,9 +96,6 @@ class _Generator(nn.Module):
         super().__init__()
         assert norm_layer in [None, 'batch_norm', 'instance_norm'], \
             "norm_layer should be None, 'batch_norm' or 'instance_norm', not {}".format(norm_layer)
-        if norm_layer == 'instance_norm':
-            raise NotImplementedError("norm_layer='instance_norm' (models.py:34-35) is not implemented by the "
-                                      "B200 engine; no shipped config uses it")
         self.norm_layer = norm_layer
         self.gpu_ids = gpu_ids
         self.use_bias = bool(use_bias)
@@ -186,7 +183,7 @@ class _Generator(nn.Module):
             cfg.use_bias = int(self.use_bias)
             cfg.tanh = int(self.tanh)
             cfg.append_smoothers = int(self.append_smoothers)
-            cfg.norm = capi.NORM_BATCH if self.norm_layer == 'batch_norm' else capi.NORM_NONE
+            cfg.norm = {'batch_norm': capi.NORM_BATCH, 'instance_norm': capi.NORM_INSTANCE}.get(self.norm_layer, capi.NORM_NONE)
             cfg.precision = capi.PRECISIONS[self.precision]
             cfg.device = idx
             h = C.c_void_p()
@@ -224,6 +221,10 @@ class _Generator(nn.Module):
         if self.training:
             raise RuntimeError("drawingspinup_b200 generators are inference-only: call .eval() first (the reference scripts do, "
                                "test_stage1.py:48); training, trainers.py:90-108, is out of scope")
+        if self._KIND == capi.KIND_GENERATORJ_RIC and self.norm_layer is None:
+            # same failure as the reference: GeneratorJ_RIC.forward indexes self.conv0[2] (models.py:303), which does not
+            # exist without a norm module - norm_layer=None is only a runnable configuration for GeneratorJ
+            raise IndexError("index 2 is out of range (GeneratorJ_RIC.forward with norm_layer=None, models.py:303)")
 
     # ------------------------------------------------------------------ reference API
     def forward(self, x: torch.Tensor) -> torch.Tensor:

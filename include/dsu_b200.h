@@ -41,7 +41,7 @@ extern "C" {
 
 #define DSU_NORM_NONE 0
 #define DSU_NORM_BATCH 1
-#define DSU_NORM_INSTANCE 2   /* accepted by the reference ctor (models.py:34-35); DSU_E_NOTIMPL here */
+#define DSU_NORM_INSTANCE 2   /* nn.InstanceNorm2d defaults (models.py:34-35): statistics per (frame, channel), no state-dict keys */
 
 typedef struct dsu_engine* dsu_handle;
 

@@ -217,6 +217,47 @@ def test_split_fp16_stage2_plan_variants(dev, env, monkeypatch):
     assert (y0 - ref).abs().max().item() < TOL and (y1 - ref).abs().max().item() < TOL
 
 
+# ------------------------------------------------------------------ norm_layer variants of the constructor (models.py:29-35)
+def _norm_model(stage, dev, norm, precision="fp16x3", blocks=2, seed=91):
+    cls = dsu.GeneratorJ_RIC if stage == 1 else dsu.GeneratorJ
+    args = dict(DEFAULT_ARGS, resnet_blocks=blocks, norm_layer=norm)
+    sd = synth.to_torch_state_dict(synth.make_state_dict(stage, seed=seed, resnet_blocks=blocks, out_gain=0.25, norm=norm or "none"))
+    m = cls(precision=precision, **args)
+    m.load_state_dict(sd)
+    cfg = dict(rp.default_config(stage), resnet_blocks=blocks, norm=norm)
+    return m.to(dev).eval(), sd, cfg
+
+
+@pytest.mark.parametrize("norm,stage", [("instance_norm", 1), ("instance_norm", 2), (None, 2)])
+def test_norm_layer_variants_match_reference_golden(dev, golden_dir, norm, stage):
+    """nn.InstanceNorm2d (statistics per frame and channel over H x W, no state) between every convolution and its activation -
+    the engine leaves the raw convolution output in an fp32 scratch buffer and normalises in a separate pass (frames.cu) -
+    and norm_layer=None, against vectors recorded from the live reference."""
+    g = np.load(os.path.join(golden_dir, "generator_%s_stage%d.npz" % (norm or "no_norm", stage)))
+    m, _, _ = _norm_model(stage, dev, norm)
+    with torch.no_grad():
+        y = m(torch.from_numpy(g["x"]).to(dev)).cpu().numpy()
+    assert np.abs(y - g["y"]).max() < TOL
+
+
+@pytest.mark.parametrize("stage", [1, 2])
+@pytest.mark.parametrize("shape", [(3, 72, 100), (1, 132, 68)])
+def test_instance_norm_ragged_shapes_and_batch_independence(dev, stage, shape):
+    b, h, w = shape
+    m, sd, cfg = _norm_model(stage, dev, "instance_norm")
+    x = _frames_tensor(b, h, w, seed=41, stage=stage)
+    with torch.no_grad():
+        y = m(x.to(dev)).cpu()
+        ref = rp.generator_j_ric_forward(sd, x, cfg, use_torchvision=True) if stage == 1 else rp.generator_j_forward(sd, x, cfg)
+        assert (y - ref).abs().max().item() < TOL
+        y0 = m(x[:1].to(dev)).cpu()                       # statistics are per frame: a frame does not see its batch mates
+    assert (y0 - y[:1]).abs().max().item() < 1e-4
+    m16, _, _ = _norm_model(stage, dev, "instance_norm", precision="fp16")
+    with torch.no_grad():
+        y16 = m16(x.to(dev)).cpu()
+    assert (y16 - ref).abs().max().item() < TOL_FP16
+
+
 # ------------------------------------------------------------------ tensor-memory RIC kernel configurations
 def test_tensor_memory_kernel_issuer_and_stage_knobs(dev):
     """The tensor-memory RIC kernel with 1 / 3 issuing warps and the minimum weight ring gives the same result as the default

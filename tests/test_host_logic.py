@@ -74,8 +74,12 @@ def test_variant_config_keys():
 
 
 def test_unsupported_options_fail_loudly():
-    with pytest.raises(NotImplementedError):
-        dsu.GeneratorJ(norm_layer="instance_norm")
+    m = dsu.GeneratorJ(norm_layer="instance_norm", **DEFAULT_ARGS)         # nn.InstanceNorm2d has no state: only conv_11_a.2 remains
+    keys = list(m.state_dict().keys())
+    assert keys == list(synth.make_state_dict(2, norm="instance_norm").keys()) and len(keys) == 29
+    assert list(dsu.GeneratorJ_RIC(norm_layer=None, **DEFAULT_ARGS).state_dict().keys()) == list(synth.make_state_dict(1, norm="none").keys())
+    with torch.no_grad(), pytest.raises(IndexError):                          # the reference's own stage-1 forward fails the same way
+        dsu.GeneratorJ_RIC(norm_layer=None, **DEFAULT_ARGS).eval()(torch.zeros(1, 6, 16, 16))
     with pytest.raises(AssertionError):
         dsu.GeneratorJ(norm_layer="layer_norm")
     with pytest.raises(ValueError):
@@ -198,8 +202,8 @@ def test_c_abi_rejects_bad_arguments_without_gpu(built_lib):
     cfg.kind = 7
     assert lib.dsu_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
     cfg.kind = capi.KIND_GENERATORJ
-    cfg.norm = capi.NORM_INSTANCE
-    assert lib.dsu_create(ctypes.byref(cfg), ctypes.byref(h)) == capi.E_NOTIMPL
+    cfg.norm = 3                                        # DSU_NORM_NONE / BATCH / INSTANCE are 0 / 1 / 2
+    assert lib.dsu_create(ctypes.byref(cfg), ctypes.byref(h)) == -1 and "norm" in capi.last_error()
     assert lib.dsu_forward(None, None, 1, 16, 16, None, None) < 0
     assert lib.dsu_to_image_space(None, None, 4, None) < 0
     lib.dsu_destroy(None)                               # no-op, must not crash
