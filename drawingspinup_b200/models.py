@@ -163,7 +163,17 @@ class _Generator(nn.Module):
             pass
 
     def _signature(self):
-        return tuple((k, v.data_ptr(), v._version) for k, v in self.state_dict(keep_vars=True).items())
+        # identity + version of every state-dict tensor: a changed weight (load_state_dict, in-place edit, .to()) re-packs.
+        # The tensor list is cached - walking state_dict() costs ~0.2 ms per forward on the batch-1 script path - and dropped
+        # whenever .to() / .cuda() / .half() may have replaced buffer objects (_apply).
+        ts = self.__dict__.get("_sig_tensors")
+        if ts is None:
+            ts = self.__dict__["_sig_tensors"] = list(self.state_dict(keep_vars=True).values())
+        return tuple((v.data_ptr(), v._version) for v in ts)
+
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__.pop("_sig_tensors", None)
+        return super()._apply(fn, *args, **kwargs)
 
     def _engine(self, device: torch.device):
         """Create the engine for ``device`` if needed and (re)upload weights when any changed."""
