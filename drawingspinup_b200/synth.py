@@ -17,15 +17,19 @@ DEFAULT_FILTERS = (32, 64, 128, 128, 128, 64)
 
 
 def _lowfreq(rng, n, h, w, ch, grid=8):
-    """[n,h,w,ch] smooth noise in [0,1]: grid x grid control points, bilinear upsampling."""
+    """[n,h,w,ch] smooth noise in [0,1]: grid x grid control points, bilinear upsampling.  (Frame by frame: the same fp32
+    operations in the same order as the whole-array form, ~5x faster because the temporaries stay in cache - the synthetic
+    clips of the multi-GPU bench configs are hundreds of frames per rank.)"""
     ctl = rng.random((n, grid + 1, grid + 1, ch), dtype=np.float32)
     ys = np.linspace(0, grid, h, endpoint=False, dtype=np.float32)
     xs = np.linspace(0, grid, w, endpoint=False, dtype=np.float32)
     y0 = ys.astype(np.int64); x0 = xs.astype(np.int64)
-    fy = (ys - y0)[None, :, None, None]; fx = (xs - x0)[None, None, :, None]
-    a = ctl[:, y0][:, :, x0]; b = ctl[:, y0][:, :, x0 + 1]
-    c = ctl[:, y0 + 1][:, :, x0]; d = ctl[:, y0 + 1][:, :, x0 + 1]
-    return (a * (1 - fy) * (1 - fx) + b * (1 - fy) * fx + c * fy * (1 - fx) + d * fy * fx).astype(np.float32)
+    fy = (ys - y0)[:, None, None]; fx = (xs - x0)[None, :, None]
+    out = np.empty((n, h, w, ch), np.float32)
+    for i in range(n):
+        r0 = ctl[i][y0]; r1 = ctl[i][y0 + 1]
+        out[i] = r0[:, x0] * (1 - fy) * (1 - fx) + r0[:, x0 + 1] * (1 - fy) * fx + r1[:, x0] * fy * (1 - fx) + r1[:, x0 + 1] * fy * fx
+    return out
 
 
 def make_frames(n_frames: int, height: int = 512, width: int = 512, seed: int = 1234
