@@ -362,7 +362,7 @@ def main():
     import torch
     import torch.distributed as dist
     from drawingspinup_b200 import synth
-    from drawingspinup_b200.pipeline import StylizationPipeline, broadcast_state_dict, shard_range
+    from drawingspinup_b200.pipeline import StylizationPipeline, assign_work, broadcast_state_dict
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the B200 engine has no CPU fallback (use --impl reference for the CPU path)")
@@ -383,14 +383,8 @@ def main():
         frames_of = {0: F}
         seeds = {0: 1234 + rank}
     else:
-        per_char = total_frames // n_chars
-        if n_chars > 1:                                   # character -> GPU: rank r owns characters r, r + world, ...
-            my_chars = [c for c in range(n_chars) if c % world == rank]
-            frames_of = {c: per_char for c in my_chars}
-        else:
-            lo, hi = shard_range(total_frames, rank, world)
-            my_chars = [0]
-            frames_of = {0: hi - lo}
+        frames_of = assign_work(total_frames, n_chars, rank, world)   # character -> GPU, or a frame shard of the one clip
+        my_chars = sorted(frames_of)
         seeds = {c: 1234 + 17 * c + rank for c in my_chars}
     my_frames = sum(frames_of.values())
     all_frames = my_frames

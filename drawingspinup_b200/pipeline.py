@@ -32,6 +32,20 @@ def shard_range(n_frames: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def assign_work(total_frames: int, n_chars: int, rank: int, world: int):
+    """Frames of this rank as ``{character: frame count}``.  One character (weights broadcast once): contiguous
+    frame shard of the clip.  Several characters - one checkpoint each, README.md:210 "train a model for each sample" -:
+    character c goes to rank ``c % world`` with all of its ``total_frames // n_chars`` frames, nothing is broadcast.
+    The shares tile the work exactly: summed over the ranks they give ``total_frames`` (of whole characters)."""
+    if n_chars < 1 or world < 1 or not (0 <= rank < world) or total_frames < 0:
+        raise ValueError("bad work assignment arguments")
+    if n_chars == 1:
+        lo, hi = shard_range(total_frames, rank, world)
+        return {0: hi - lo}
+    per_char = total_frames // n_chars
+    return {c: per_char for c in range(n_chars) if c % world == rank}
+
+
 def broadcast_state_dict(sd: Optional[Dict[str, torch.Tensor]], src: int = 0, device=None
                          ) -> "OrderedDict[str, torch.Tensor]":
     """The single collective of the path: rank ``src`` holds the per-character checkpoint

@@ -61,3 +61,42 @@ def test_broadcast_without_process_group_is_identity():
     sd = synth.to_torch_state_dict(synth.make_state_dict(1, seed=2))
     out = broadcast_state_dict(sd)
     assert list(out.keys()) == list(sd.keys()) and all(out[k] is sd[k] for k in sd)
+
+
+def _char_worker(rank, world, port, ret):
+    """BASELINE configs[3] on CPU: 8 characters (distinct checkpoints) -> ranks, nothing broadcast; every rank reports which
+    characters it owns, a checksum of each one's weights and its frame count; all-reduced totals must tile the job."""
+    from drawingspinup_b200.pipeline import assign_work
+    dist.init_process_group("gloo", rank=rank, world_size=world, init_method="tcp://127.0.0.1:%d" % port)
+    try:
+        share = assign_work(8 * 16, 8, rank, world)
+        owned = torch.zeros(8, dtype=torch.int64)
+        sums = torch.zeros(8, dtype=torch.float64)
+        for c, nf in share.items():
+            sd = synth.make_state_dict(1, seed=1234 + c, resnet_blocks=1)         # what bench.py's _weights(1234 + c) loads
+            owned[c] += nf
+            sums[c] = float(sum(np.asarray(v, dtype=np.float64).sum() for v in sd.values()))
+        dist.all_reduce(owned)
+        dist.all_reduce(sums)
+        ret[rank] = (sorted(share), owned.tolist(), [round(v, 6) for v in sums.tolist()])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_character_to_rank_assignment_world2():
+    from drawingspinup_b200.pipeline import assign_work
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_char_worker, args=(world, port, ret), nprocs=world, join=True)
+        r0, r1 = ret[0], ret[1]
+    assert r0[0] == [0, 2, 4, 6] and r1[0] == [1, 3, 5, 7]
+    assert r0[1] == r1[1] == [16] * 8                                   # every character's frames counted exactly once
+    assert r0[2] == r1[2] and len(set(r0[2])) == 8                      # eight distinct checkpoints, each built by one rank
+    # shapes of the job the planner must handle
+    for world in (1, 2, 3, 8, 16):
+        shares = [assign_work(1024, 8, r, world) for r in range(world)]
+        assert sum(sum(s.values()) for s in shares) == 1024 and sorted(c for s in shares for c in s) == list(range(8))
+    assert [assign_work(10, 1, r, 4) for r in range(4)] == [{0: 3}, {0: 3}, {0: 2}, {0: 2}]
+    with pytest.raises(ValueError):
+        assign_work(8, 2, 2, 2)
