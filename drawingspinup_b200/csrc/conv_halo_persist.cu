@@ -1,13 +1,15 @@
-// Persistent variant of the halo-reuse convolution (conv_halo.cu): one CTA per SM walks a static list of
-// output tiles; the accumulators are double-buffered in TMEM so the epilogue of tile i (4 dedicated warps)
-// overlaps the halo staging, weight streaming and MMAs of tile i+1, and the prologue (barrier init, TMEM
-// allocation, parameter load) is paid once per SM instead of once per tile.  Pays off for the short-K
-// layers (3x3, N=64 smoothers; residual trunk) where a non-persistent CTA spends more cycles in
-// prologue + epilogue than in its main loop (profiles/: conv_11_a 0.9 -> see DESIGN.md section 7).
+// Halo-reuse convolution for the plain (stage-2) stride-1 layers, persistent: one CTA per SM walks a static list of output
+// tiles.  A (16 + 2p) x (8 ns + 2p)-pixel halo tile per 64-channel block (split-fp16: 32 channels as [hi | lo]) is staged once
+// in shared memory, one pixel per 128-byte row, and EVERY tap reads a shifted window of it through its UMMA descriptor (start
+// row = kh W + kw + 8 s, 8-row-group stride = W x 128 B; tools/umma_probe.cu established that the descriptor reads linear rows
+// from any 128-byte-aligned start and swizzles on absolute address bits).  The accumulators are double-buffered in TMEM so the
+// epilogue of tile i (4 dedicated warps) overlaps the halo staging, weight streaming and MMAs of tile i + 1, and the prologue
+// (barrier init, TMEM allocation, parameter load) is paid once per SM instead of once per tile.
 //
-// Roles: warps 0-3 halo producers, warps 4-7 epilogue, warps 8-11 MMA issuers (sub-tile x K-split, private
-// weight rings - see conv_halo.cu), warp 12 weight loader.  TMEM: nsets (2, or 1 when two do not fit) x (ns*ks) accumulators
-// x Cout columns (2 Cout in the n128 form of the split-fp16 Cout = 64 layers, see ConvParams::n128).
+// Roles: warps 0-3 halo producers, warps 4-7 epilogue, warps 8-11 MMA issuers (sub-tile x K-split; every K-split group has a
+// private weight ring - a ring shared by consumer warps lets one that is a revolution ahead pass a parity wait on the previous
+// phase), warp 12 weight loader.  TMEM: nsets (2, or 1 when two do not fit) x (ns*ks) accumulators x Cout columns (2 Cout in
+// the n128 form of the split-fp16 Cout = 64 layers, see ConvParams::n128).
 #include "conv_device.cuh"
 
 namespace dsu {

@@ -1,7 +1,7 @@
 // RIC (rotation-invariant deformable) convolution of stage 1 (training/models.py:302-351 with the offset field of
 // generate_coordinates, :551-604) with the blended A operand in TENSOR MEMORY.
 //
-// Why (round-2 measurements, profiles/r02b_umma_ts_probe.log, r01n_ric_persist_upconv1.ncu-rep): the round-1 kernel wrote
+// Why (round-2 measurements, profiles/r02b_umma_ts_probe.log, the r01n_ric_persist_upconv1 row of profiles/r01_kernels.csv): the round-1 kernel wrote
 // the 9 blended taps of every (pixel, 8 channels) item to shared memory and let tcgen05.mma read them back - 144 KB of
 // single-buffered A tiles per 64-channel block (production and MMAs serialised), three shared-memory passes over the same
 // bytes (neighbour reads, A writes, A reads: the SM's 128 B/clk were the limit before the tensor pipe), and N = 64 layers
@@ -400,9 +400,7 @@ conv_ric_tm_kernel(const __grid_constant__ TmParams P) {
 #pragma unroll
                             for (int t = 0; t < 9; ++t) {
                                 tmem_st2(cb + t * 8, out[t].x, out[t].y);
-#ifndef DSU_TM_EXPERIMENT_SKIP_LO
                                 tmem_st2(cb + 72 + t * 8, out[t].z, out[t].w);
-#endif
                             }
                         }
                     }

@@ -79,9 +79,10 @@ int dsu_loaded_keys(dsu_handle h);
  * tensor-core tiles, upload.  Requires every expected key (strict=True semantics). */
 int dsu_finalize(dsu_handle h, void* stream);
 
-/* Development / test hook, no counterpart in the reference: kernel-selection knobs of this handle ("first", "ric_first",
- * "ric_persist", "halo_ns", ... - engine.cu Knobs).  Their defaults are read once from the environment (DSU_<NAME>) by
- * dsu_create; "subpixel" shapes the launch plan and can only be set through the environment (DSU_E_STATE otherwise). */
+/* Development / test hook, no counterpart in the reference: kernel-selection knobs of this handle ("first", "halo_ns",
+ * "halo_ks", "tm_ni", "tm_sb", "derive_edge", "tm_trace", ... - engine.cu Knobs).  Their defaults are read once from the
+ * environment (DSU_<NAME>) by dsu_create; "subpixel" and "n128" shape the launch plan / the weight packing and can only be set
+ * through the environment (DSU_E_STATE otherwise). */
 int dsu_set_knob(dsu_handle h, const char* name, int32_t value);
 
 /* generate_coordinates (models.py:551-604) is data independent; by default the engine derives the

@@ -4,7 +4,7 @@
 //   waits for each group's commit before the next (sync=1: a 1-deep pipeline; sync=0: commits are
 //   only tracked), the number of distinct accumulators cycled through, and CTAs per SM.
 // Used to separate "tensor pipe / smem operand bandwidth" limits from per-chunk synchronisation cost
-// in conv_umma.cu / conv_halo.cu.
+// in conv_umma.cu / conv_halo_persist.cu.
 //   build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o umma_rate.bin umma_rate.cu
 #include <cstdio>
 #include <vector>
