@@ -64,7 +64,7 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 template <int kSleepNs>
-__device__ __forceinline__ void mbar_wait_wd(uint32_t bar, uint32_t parity, unsigned long long* dbg, uint32_t tag, int a, int b) {
+__device__ __forceinline__ void mbar_wait_poll(uint32_t bar, uint32_t parity, unsigned long long* dbg, uint32_t tag, int a, int b) {
     if (mbar_test(bar, parity)) return;
     long long t0 = 0;
     uint32_t iter = 0;
@@ -84,6 +84,14 @@ __device__ __forceinline__ void mbar_wait_wd(uint32_t bar, uint32_t parity, unsi
             if (dt > 2800000000LL) __trap();
         }
     }
+}
+
+// Every wait of this kernel is made by all 32 lanes of a warp; lanes may leave the polling loop in different iterations, and
+// what follows a wait is often a warp-collective .sync.aligned tcgen05 instruction that must not be reached diverged.
+template <int kSleepNs>
+__device__ __forceinline__ void mbar_wait_wd(uint32_t bar, uint32_t parity, unsigned long long* dbg, uint32_t tag, int a, int b) {
+    mbar_wait_poll<kSleepNs>(bar, parity, dbg, tag, a, b);
+    __syncwarp();
 }
 
 template <int kRegs>
@@ -442,6 +450,7 @@ conv_ric_tm_kernel(const __grid_constant__ TmParams P) {
             // stage 1 only needs the plain variants (no activation / ReLU / LeakyReLU; never a second affine or a lo plane)
             epilogue_row<0x0007u>(p, s_par, t_acc, n, ty0 + (r >> 4), tx0 + (r & 15), 0, 1, 0, 1);
             tr.ev(8, it);
+            __syncwarp();            // lanes of pixels outside the image took a shorter path through the epilogue
             for (int c = 0; c < C; c += 32) tmem_st_zero32(t_acc + c);
             tmem_st_wait();
             tc_fence_before();
