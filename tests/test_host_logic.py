@@ -313,3 +313,31 @@ def test_n128_issue_form_of_the_split_fp16_product():
     assert np.allclose(got, three, rtol=0, atol=1e-12)
     exact = f(a) @ f(w).T
     assert np.abs(got - exact).max() < 2.0 ** -20 * np.abs(f(a)).max() * np.abs(f(w)).max() * 32
+
+
+def test_work_assignment_properties():
+    """shard_range / assign_work (pipeline.py) over many job shapes: the shares are contiguous, ordered, differ by at
+    most one frame, and tile the clip exactly; characters land on exactly one rank each."""
+    from hypothesis import given, settings, strategies as st
+    from drawingspinup_b200.pipeline import assign_work, shard_range
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(0, 5000), st.integers(1, 64))
+    def frames(n, world):
+        spans = [shard_range(n, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+        assert [assign_work(n, 1, r, world) for r in range(world)] == [{0: s} for s in sizes]
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(2, 40), st.integers(1, 64), st.integers(0, 300))
+    def characters(n_chars, world, per_char):
+        shares = [assign_work(n_chars * per_char, n_chars, r, world) for r in range(world)]
+        owners = sorted(c for s in shares for c in s)
+        assert owners == list(range(n_chars)) and all(v == per_char for s in shares for v in s.values())
+        assert max(len(s) for s in shares) - min(len(s) for s in shares) <= 1
+
+    frames()
+    characters()
